@@ -1,0 +1,110 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in this container.
+
+    PYTHONPATH=/root/reference python oracle/make_golden.py
+
+Imports only reference modules that are importable without diffusers:
+afldm.af_libs.ideal_lpf, afldm.af_libs.torch_utils.ops.upfirdn2d, afldm.shift_utils.{shifters,metrics}.
+`/root/reference` cannot travel to the GPU box, so the vectors are committed as small fixtures.
+Test infrastructure only.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+sys.path.insert(0, "/root/reference")
+
+from afldm.af_libs import ideal_lpf as R                      # noqa: E402
+from afldm.af_libs.torch_utils.ops import upfirdn2d as RU     # noqa: E402
+from afldm.shift_utils import metrics as RM                   # noqa: E402
+from afldm.shift_utils import shifters as RS                  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+
+def randn(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def main():
+    # ---- masks (a1, a2)
+    masks = {}
+    for n in (2, 4, 6, 8, 12, 16, 32, 64, 128):
+        masks[f"lpf_{n}"] = R.create_lpf_rect(n, 0.5).numpy()
+        masks[f"recon_{n}"] = R.create_recon_rect(n, 0.5).numpy()
+    masks["recon_16_c8"] = R.create_recon_rect(16, 1 / 8).numpy()
+    masks["recon_64_c8"] = R.create_recon_rect(64, 1 / 8).numpy()
+    np.savez_compressed(os.path.join(OUT, "masks.npz"), **masks)
+
+    # ---- ideal ops (a3-a6): input seeds/shapes + outputs
+    ops = {}
+    cases = {"s2": ((2, 3, 2, 2), 11), "s4": ((2, 5, 4, 4), 12), "s8": ((2, 3, 8, 8), 13),
+             "s16": ((1, 4, 16, 16), 14), "s32": ((1, 3, 32, 32), 15), "s64": ((1, 3, 64, 64), 1234),
+             "s6": ((1, 2, 6, 6), 16)}
+    up, lpf = R.UpsampleRFFT(), R.LPF_RFFT(0.5)
+    for name, (shape, seed) in cases.items():
+        x = randn(shape, seed)
+        ops[f"{name}_seed"] = np.array(seed)
+        ops[f"{name}_x"] = x.numpy()
+        u = up(x)
+        ops[f"{name}_up2"] = u.numpy()
+        ops[f"{name}_lpf_down2"] = lpf(x.clone())[:, :, ::2, ::2].contiguous().numpy()
+        ops[f"{name}_filtered_silu"] = lpf(torch.nn.functional.silu(u))[:, :, ::2, ::2].contiguous().numpy()
+    x8 = randn((1, 4, 8, 8), 21)
+    ops["up8_x"] = x8.numpy()
+    ops["up8_y"] = R.UpsampleRFFT(8)(x8).numpy()
+    ops["subpix_x"] = x8.numpy()
+    ops["subpix_y"] = R.subpixel_shift(x8, up=2, shift_x=1, shift_y=1).contiguous().numpy()
+    np.savez_compressed(os.path.join(OUT, "ideal_ops.npz"), **ops)
+
+    # ---- upfirdn2d (a16, BASELINE config #1)
+    ud = {}
+    x = randn((1, 3, 64, 64), 1234)
+    f = RU.setup_filter([1, 3, 3, 1])
+    ud["x"] = x.numpy()
+    ud["f1331"] = f.numpy()
+    ud["up2"] = RU.upsample2d(x, f, up=2, impl="ref").numpy()
+    ud["down2"] = RU.downsample2d(x, f, down=2, impl="ref").numpy()
+    ud["filter2d"] = RU.filter2d(x, f, impl="ref").numpy()
+    f12 = RU.setup_filter([1, 2, 4, 7, 9, 11, 11, 9, 7, 4, 2, 1])      # separable (>= 8 taps)
+    ud["f12"] = f12.numpy()
+    ud["up2_f12"] = RU.upsample2d(x, f12, up=2, impl="ref").numpy()
+    xs = randn((2, 2, 9, 7), 5)
+    fa = RU.setup_filter([1, 2, 5], normalize=True)
+    ud["xs"] = xs.numpy()
+    ud["fa"] = fa.numpy()
+    ud["gen"] = RU.upfirdn2d(xs, fa, up=3, down=2, padding=[2, 1, 0, 3], flip_filter=True, gain=1.7, impl="ref").numpy()
+    ud["gen_noflip"] = RU.upfirdn2d(xs, fa, up=2, down=1, padding=[1, 1, 2, 0], flip_filter=False, gain=1.0, impl="ref").numpy()
+    ud["crop"] = RU.upfirdn2d(xs, fa, up=2, down=1, padding=[-1, 2, 1, -2], impl="ref").numpy()
+    np.savez_compressed(os.path.join(OUT, "upfirdn2d.npz"), **ud)
+
+    # ---- shift harness (a15)
+    sh = {}
+    lat = randn((1, 4, 32, 32), 77)
+    sh["lat"] = lat.numpy()
+    shifter = RS.ImageShifter("ideal_crop", 8)
+    for k, (ti, tj) in enumerate([(0, 1 / 8), (0, 5 / 8), (0.25, 1.0), (-0.375, 2.125)]):
+        w, m = shifter.shift(lat, ti, tj)
+        sh[f"shift{k}_t"] = np.array([ti, tj])
+        sh[f"shift{k}_img"] = w.contiguous().numpy()
+        sh[f"shift{k}_mask"] = m.numpy()
+    a, b = randn((2, 3, 16, 16), 3), randn((2, 3, 16, 16), 4)
+    m = RS.gen_valid_mask(a.shape, 2.5, -1.25)
+    sh["m_a"], sh["m_b"], sh["m_mask"] = a.numpy(), b.numpy(), m.numpy()
+    sh["mask_mse"] = RM.mask_mse(a, b, m).numpy()
+    sh["mask_psnr"] = RM.mask_psnr(a, b, m).numpy()
+    sh["psnr"] = RM.psnr(a, b).numpy()
+    np.savez_compressed(os.path.join(OUT, "shift.npz"), **sh)
+
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    main()
