@@ -1,0 +1,158 @@
+// fp32 scaled-dot-product attention (flash-style online softmax), separate K/V source.
+//
+// Replaces F.scaled_dot_product_attention inside diffusers AttnProcessor2_0 as used by the
+// reference including the cross-frame case of
+// afldm/pipelines/cross_frame_attn.py:79-97, where K/V come from a stored reference-frame map
+// with a smaller batch (batch b reads K/V batch b / (B / Bkv)).
+//
+// One thread owns one query row: q, the output accumulator and the running max / sum live in
+// registers.  K and V tiles of 64 keys are staged in shared memory and read as warp-wide
+// broadcasts (all threads of a CTA walk the keys in lock-step), so shared-memory traffic is
+// one 128-bit broadcast per 4 FMAs.  Scores are kept in the exp2 domain (q is pre-multiplied by
+// scale * log2 e); the running max is updated once per 8 keys.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace afldm {
+namespace {
+
+constexpr int ATT_KT = 64;   // keys per shared-memory tile
+constexpr int ATT_KC = 8;    // keys per online-softmax update
+constexpr int ATT_THREADS = 128;
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
+                 const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
+                 int Bkv_rep, int Nq, int Nk, float qscale) {
+    constexpr int D4 = D / 4;
+    __shared__ float4 Ks[ATT_KT * D4];
+    __shared__ float4 Vs[ATT_KT * D4];
+    const int b = blockIdx.z, head = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = r < Nq;
+    const int bkv = b / Bkv_rep;
+
+    float qr[D], acc[D];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + (valid ? r : 0)) * q_pitch + head * D);
+#pragma unroll
+        for (int t = 0; t < D4; ++t) {
+            const float4 t4 = qp[t];
+            qr[4 * t + 0] = t4.x * qscale;
+            qr[4 * t + 1] = t4.y * qscale;
+            qr[4 * t + 2] = t4.z * qscale;
+            qr[4 * t + 3] = t4.w * qscale;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < D; ++t) acc[t] = 0.f;
+    float mrun = -INFINITY, lrun = 0.f;
+
+    const float* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    const float* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
+
+    for (int k0 = 0; k0 < Nk; k0 += ATT_KT) {
+        const int nk = min(ATT_KT, Nk - k0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nk * D4; idx += blockDim.x) {
+            const int key = idx / D4, t = idx - key * D4;
+            Ks[idx] = *reinterpret_cast<const float4*>(kbase + (size_t)(k0 + key) * kv_pitch + 4 * t);
+            Vs[idx] = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * kv_pitch + 4 * t);
+        }
+        __syncthreads();
+        for (int kk = 0; kk < nk; kk += ATT_KC) {
+            float s[ATT_KC];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < ATT_KC; ++j) {
+                float d = 0.f;
+                if (kk + j < nk) {
+                    const float4* kr = Ks + (kk + j) * D4;
+#pragma unroll
+                    for (int t = 0; t < D4; ++t) {
+                        const float4 kv4 = kr[t];
+                        d = fmaf(qr[4 * t + 0], kv4.x, d);
+                        d = fmaf(qr[4 * t + 1], kv4.y, d);
+                        d = fmaf(qr[4 * t + 2], kv4.z, d);
+                        d = fmaf(qr[4 * t + 3], kv4.w, d);
+                    }
+                } else {
+                    d = -INFINITY;
+                }
+                s[j] = d;
+                mx = fmaxf(mx, d);
+            }
+            const float mnew = fmaxf(mrun, mx);
+            const float corr = exp2f(mrun - mnew);
+            lrun *= corr;
+#pragma unroll
+            for (int t = 0; t < D; ++t) acc[t] *= corr;
+#pragma unroll
+            for (int j = 0; j < ATT_KC; ++j) {
+                if (kk + j < nk) {
+                    const float p = exp2f(s[j] - mnew);
+                    lrun += p;
+                    const float4* vr = Vs + (kk + j) * D4;
+#pragma unroll
+                    for (int t = 0; t < D4; ++t) {
+                        const float4 vv = vr[t];
+                        acc[4 * t + 0] = fmaf(p, vv.x, acc[4 * t + 0]);
+                        acc[4 * t + 1] = fmaf(p, vv.y, acc[4 * t + 1]);
+                        acc[4 * t + 2] = fmaf(p, vv.z, acc[4 * t + 2]);
+                        acc[4 * t + 3] = fmaf(p, vv.w, acc[4 * t + 3]);
+                    }
+                }
+            }
+            mrun = mnew;
+        }
+    }
+    if (valid) {
+        const float inv = 1.0f / lrun;
+        float4* op = reinterpret_cast<float4*>(o + ((size_t)b * Nq + r) * o_pitch + head * D);
+#pragma unroll
+        for (int t = 0; t < D4; ++t)
+            op[t] = make_float4(acc[4 * t] * inv, acc[4 * t + 1] * inv, acc[4 * t + 2] * inv, acc[4 * t + 3] * inv);
+    }
+}
+
+template <int D>
+int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
+           int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+    const int threads = Nq >= ATT_THREADS ? ATT_THREADS : ((Nq + 31) / 32) * 32;
+    const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
+    attention_kernel<D><<<dim3(ceil_div(Nq, threads), heads, B), threads, 0, st>>>(
+        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
+    return launched();
+}
+
+}  // namespace
+}  // namespace afldm
+
+using namespace afldm;
+
+extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
+                                   float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                                   afldm_stream_t stream) {
+    if (q == nullptr || k == nullptr || v == nullptr || o == nullptr) return AFLDM_E_ARG;
+    if (B <= 0 || Bkv <= 0 || Nq <= 0 || Nk <= 0 || heads <= 0 || d <= 0) return AFLDM_E_ARG;
+    if (B % Bkv != 0) return AFLDM_E_SHAPE;
+    if (d % 4 != 0 || q_pitch % 4 != 0 || kv_pitch % 4 != 0 || o_pitch % 4 != 0) return AFLDM_E_SHAPE;
+    if (q_pitch < heads * d || kv_pitch < heads * d || o_pitch < heads * d) return AFLDM_E_ARG;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return AFLDM_E_ARG;
+    cudaStream_t st = as_stream(stream);
+#define AFLDM_ATT_CASE(D) \
+    case D: return launch<D>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    switch (d) {
+        AFLDM_ATT_CASE(8)
+        AFLDM_ATT_CASE(16)
+        AFLDM_ATT_CASE(24)
+        AFLDM_ATT_CASE(32)
+        AFLDM_ATT_CASE(40)
+        AFLDM_ATT_CASE(48)
+        AFLDM_ATT_CASE(64)
+        default: return AFLDM_E_NOKERNEL;
+    }
+#undef AFLDM_ATT_CASE
+}

@@ -1,0 +1,48 @@
+// Shared helpers for the afldm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/afldm_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "afldm_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace afldm {
+
+// Host-side count of kernels launched through the C ABI (afldm_launch_count()).
+void note_launch(int n = 1);
+
+// Every ABI entry point ends with this: count the launch, surface launch errors.
+inline int launched(int n = 1) {
+    note_launch(n);
+    return (int)cudaGetLastError();
+}
+
+inline cudaStream_t as_stream(afldm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + expf(-z)); }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float z) {
+    if constexpr (ACT == AFLDM_ACT_SILU) return silu_f(z);
+    return z;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace afldm

@@ -1,0 +1,233 @@
+// Small ops of one denoising step: few-row linear layers (time embedding), sinusoidal timestep
+// embedding, channel concat, NCHW <-> NHWC, the DDIM update, and StyleGAN3's upfirdn2d.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace afldm {
+namespace {
+
+// ------------------------------------------------------------------ linear on a few rows
+// y[m][n] = act_out( sum_k act_in(x[m][k]) * w[n][k] + bias[n] ),  M <= 64.
+// x is staged (activated) in shared memory; one warp per output column streams its weight row
+// with coalesced loads - the op is bound by the N*K*4 B weight stream.
+constexpr int LIN_MT = 16;  // rows handled per accumulator pass
+
+template <int ACT_IN, int ACT_OUT>
+__global__ void __launch_bounds__(256)
+linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ y, int M, int K, int N) {
+    extern __shared__ float xs[];  // [M][K]
+    for (int i = threadIdx.x; i < M * K; i += blockDim.x) xs[i] = apply_act<ACT_IN>(x[i]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int n = blockIdx.x * warps_per_block + (threadIdx.x >> 5); n < N; n += gridDim.x * warps_per_block) {
+        const float* wr = w + (size_t)n * K;
+        for (int m0 = 0; m0 < M; m0 += LIN_MT) {
+            float acc[LIN_MT];
+#pragma unroll
+            for (int i = 0; i < LIN_MT; ++i) acc[i] = 0.f;
+            for (int kk = lane; kk < K; kk += 32) {
+                const float wv = wr[kk];
+#pragma unroll
+                for (int i = 0; i < LIN_MT; ++i)
+                    if (m0 + i < M) acc[i] = fmaf(xs[(m0 + i) * K + kk], wv, acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < LIN_MT; ++i) {
+                const float s = warp_sum(acc[i]);
+                if (lane == 0 && m0 + i < M) {
+                    float r = s + (bias != nullptr ? bias[n] : 0.f);
+                    y[(size_t)(m0 + i) * N + n] = apply_act<ACT_OUT>(r);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ timestep embedding
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, kf = i % half;
+    // same fp32 operation order as the PyTorch expression exp(-ln(1e4) * k / half)
+    const float e = (-9.210340371976184f * (float)kf) / (float)half;
+    const float arg = t[b] * expf(e);
+    out[(size_t)b * dim + kf] = cosf(arg);
+    out[(size_t)b * dim + half + kf] = sinf(arg);
+}
+
+// ------------------------------------------------------------------ concat along channels
+__global__ void __launch_bounds__(256)
+concat_kernel(const float4* __restrict__ a, int Ca4, const float4* __restrict__ b, int Cb4,
+              float4* __restrict__ y, long long total4) {
+    const int C4 = Ca4 + Cb4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const long long p = i / C4;
+        const int c = (int)(i - p * C4);
+        y[i] = c < Ca4 ? a[p * Ca4 + c] : b[p * Cb4 + (c - Ca4)];
+    }
+}
+
+// ------------------------------------------------------------------ layout transposes
+// in [B][R][S] -> out [B][S][R]  (NCHW->NHWC: R = C, S = HW; NHWC->NCHW: R = HW, S = C)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int S) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float* ip = in + (size_t)b * R * S;
+    float* op = out + (size_t)b * R * S;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int r = r0 + ty + j, s = s0 + tx;
+        if (r < R && s < S) t[ty + j][tx] = ip[(size_t)r * S + s];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int s = s0 + ty + j, r = r0 + tx;
+        if (r < R && s < S) op[(size_t)s * R + r] = t[tx][ty + j];
+    }
+}
+
+// ------------------------------------------------------------------ DDIM update
+__global__ void __launch_bounds__(256)
+axpby_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out, float cx,
+             float ce, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fmaf(cx, x[i], ce * e[i]);
+}
+
+// ------------------------------------------------------------------ upfirdn2d (NCHW)
+// out[oy][ox] = gain * sum_{fy,fx} f'[fy][fx] * xup[oy*downy + fy - pady0][ox*downx + fx - padx0]
+// where xup is x zero-stuffed by (upy, upx) and f' = f flipped unless `flip`
+// (afldm/af_libs/torch_utils/ops/upfirdn2d.py:166-211; true convolution by default).
+__global__ void __launch_bounds__(256)
+upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y,
+                 int H, int W, int fh, int fw, int upx, int upy, int downx, int downy, int padx0, int pady0,
+                 int outH, int outW, int flip, float gain, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ox = (int)(i % outW);
+    const int oy = (int)((i / outW) % outH);
+    const long long plane = i / ((long long)outW * outH);
+    const float* xp = x + plane * (long long)H * W;
+    float acc = 0.f;
+    for (int fy = 0; fy < fh; ++fy) {
+        const int uy = oy * downy + fy - pady0;  // coordinate on the zero-stuffed grid
+        if (uy < 0 || uy % upy != 0) continue;
+        const int iy = uy / upy;
+        if (iy >= H) continue;
+        for (int fx = 0; fx < fw; ++fx) {
+            const int ux = ox * downx + fx - padx0;
+            if (ux < 0 || ux % upx != 0) continue;
+            const int ix = ux / upx;
+            if (ix >= W) continue;
+            const float tap = flip ? f[fy * fw + fx] : f[(fh - 1 - fy) * fw + (fw - 1 - fx)];
+            acc = fmaf(tap, xp[(size_t)iy * W + ix], acc);
+        }
+    }
+    y[i] = acc * gain;
+}
+
+inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
+    return (int)std::max<long long>(1, std::min<long long>(cap, (n + threads - 1) / threads));
+}
+
+}  // namespace
+}  // namespace afldm
+
+using namespace afldm;
+
+extern "C" int afldm_linear_rows_f32(const float* x, const float* w, const float* bias, float* y, int M, int K,
+                                     int N, int act_in, int act_out, afldm_stream_t stream) {
+    if (x == nullptr || w == nullptr || y == nullptr || M <= 0 || K <= 0 || N <= 0) return AFLDM_E_ARG;
+    if (M > 64) return AFLDM_E_SHAPE;
+    const size_t smem = (size_t)M * K * sizeof(float);
+    if (smem > 200 * 1024) return AFLDM_E_SHAPE;
+    cudaStream_t st = as_stream(stream);
+    const int blocks = std::min(ceil_div(N, 8), 148 * 4);
+#define AFLDM_LIN(AI, AO)                                                                              \
+    {                                                                                                  \
+        auto kern = linear_rows_kernel<AI, AO>;                                                        \
+        if (smem > 48 * 1024) {                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            if (e != cudaSuccess) return (int)e;                                                       \
+        }                                                                                              \
+        kern<<<blocks, 256, smem, st>>>(x, w, bias, y, M, K, N);                                       \
+        return launched();                                                                             \
+    }
+    const bool ai = act_in == AFLDM_ACT_SILU, ao = act_out == AFLDM_ACT_SILU;
+    if ((act_in != AFLDM_ACT_SILU && act_in != AFLDM_ACT_IDENTITY) ||
+        (act_out != AFLDM_ACT_SILU && act_out != AFLDM_ACT_IDENTITY))
+        return AFLDM_E_ARG;
+    if (ai && ao) AFLDM_LIN(AFLDM_ACT_SILU, AFLDM_ACT_SILU)
+    if (ai && !ao) AFLDM_LIN(AFLDM_ACT_SILU, AFLDM_ACT_IDENTITY)
+    if (!ai && ao) AFLDM_LIN(AFLDM_ACT_IDENTITY, AFLDM_ACT_SILU)
+    AFLDM_LIN(AFLDM_ACT_IDENTITY, AFLDM_ACT_IDENTITY)
+#undef AFLDM_LIN
+}
+
+extern "C" int afldm_timestep_embedding_f32(const float* t, float* out, int B, int dim, afldm_stream_t stream) {
+    if (t == nullptr || out == nullptr || B <= 0 || dim <= 0) return AFLDM_E_ARG;
+    if (dim % 2 != 0) return AFLDM_E_SHAPE;
+    const int n = B * (dim / 2);
+    timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(t, out, B, dim);
+    return launched();
+}
+
+extern "C" int afldm_concat_channels_f32(const float* a, int Ca, const float* b, int Cb, float* y,
+                                         long long pixels, afldm_stream_t stream) {
+    if (a == nullptr || b == nullptr || y == nullptr || Ca <= 0 || Cb <= 0 || pixels <= 0) return AFLDM_E_ARG;
+    if (Ca % 4 != 0 || Cb % 4 != 0) return AFLDM_E_SHAPE;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(y)) return AFLDM_E_ARG;
+    const long long total4 = pixels * (Ca + Cb) / 4;
+    concat_kernel<<<grid_for(total4), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(a), Ca / 4, reinterpret_cast<const float4*>(b), Cb / 4,
+        reinterpret_cast<float4*>(y), total4);
+    return launched();
+}
+
+static int transpose_launch(const float* x, float* y, int B, int R, int S, afldm_stream_t stream) {
+    if (x == nullptr || y == nullptr || B <= 0 || R <= 0 || S <= 0 || x == y) return AFLDM_E_ARG;
+    if (B > 65535 || ceil_div(R, 32) > 65535) return AFLDM_E_SHAPE;
+    transpose_kernel<<<dim3(ceil_div(S, 32), ceil_div(R, 32), B), 256, 0, as_stream(stream)>>>(x, y, R, S);
+    return launched();
+}
+
+extern "C" int afldm_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream) {
+    return transpose_launch(x, y, B, C, HW, stream);
+}
+
+extern "C" int afldm_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream) {
+    return transpose_launch(x, y, B, HW, C, stream);
+}
+
+extern "C" int afldm_axpby_f32(const float* x, const float* eps, float* out, float cx, float ce, long long n,
+                               afldm_stream_t stream) {
+    if (x == nullptr || eps == nullptr || out == nullptr || n <= 0) return AFLDM_E_ARG;
+    axpby_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, eps, out, cx, ce, n);
+    return launched();
+}
+
+extern "C" int afldm_upfirdn2d_f32(const float* x, const float* f, float* y, int B, int C, int H, int W, int fh,
+                                   int fw, int upx, int upy, int downx, int downy, int padx0, int padx1,
+                                   int pady0, int pady1, int flip, float gain, afldm_stream_t stream) {
+    if (x == nullptr || f == nullptr || y == nullptr) return AFLDM_E_ARG;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || fh <= 0 || fw <= 0) return AFLDM_E_ARG;
+    if (upx <= 0 || upy <= 0 || downx <= 0 || downy <= 0) return AFLDM_E_ARG;
+    const int outW = (W * upx + padx0 + padx1 - fw + downx) / downx;
+    const int outH = (H * upy + pady0 + pady1 - fh + downy) / downy;
+    if (outW < 1 || outH < 1) return AFLDM_E_SHAPE;
+    const long long total = (long long)B * C * outH * outW;
+    const int blocks = (int)((total + 255) / 256);
+    upfirdn2d_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, f, y, H, W, fh, fw, upx, upy, downx, downy, padx0,
+                                                           pady0, outH, outW, flip, gain, total);
+    return launched();
+}

@@ -1,0 +1,226 @@
+// Ideal (circular-sinc) resampling kernels: filtered activation, x2 up-sample, LPF + decimate.
+//
+// The reference runs these through cuFFT (afldm/af_libs/ideal_lpf.py:69-93, 112-134, 148-158
+// and afldm/af_modules/af_blocks.py:19-28).  Per (b, c) plane of side n the same operator is
+//      up2(x)        = U x U^T            U in R^{2n x n}: even rows identity, odd rows circulant d
+//      lpf_down2(a)  = D a D^T            D in R^{n x 2n}: D[i, m] = g[(2i - m) mod 2n]
+//      filtered_act  = D act(U x U^T) D^T
+// (SURVEY.md 8(a) identities 1-4).  Each 1-D circular convolution of one line is done by ONE
+// thread entirely in registers: the loops are fully unrolled, so every tap index is a
+// compile-time constant and the tap becomes a constant-bank operand of the FFMA - no shared
+// memory or register traffic for the filter at all.  Lines are exchanged between the row and
+// column passes through one shared-memory tile [n][2n][CG] (CG channels of the NHWC tensor,
+// channel fastest, row pitch padded by CG words so that every pass is bank-conflict free).
+//
+//   pass 1  thread (c, i):  row i of x  ->  row i of T = x U^T                 (n^2 FMA)
+//   pass 2  thread (c, jj): column jj of T -> column of Z = U T, act()          (n^2 FMA)
+//   pass 3  same thread:    column of A -> column jj of Y1 = D A  (in place)   (2 n^2 FMA)
+//   pass 4  thread (c, i):  row i of Y1 -> row i of y = Y1 D^T                 (2 n^2 FMA)
+//
+// Algorithmic HBM traffic: filtered_act 8 B/element, up2 20 B per input element,
+// lpf_down2 5 B per input element (fp32).
+#include "common.cuh"
+#include "taps.inc"
+
+namespace afldm {
+namespace {
+
+enum { MODE_FACT = 0, MODE_UP2 = 1, MODE_DOWN2 = 2 };
+
+// o[i] = sum_j d[(i - j) mod N] x[j]
+template <int N>
+__device__ __forceinline__ void up_odd(const float (&x)[N], float (&o)[N]) {
+    constexpr int IB = N >= 4 ? 4 : N;  // independent accumulators for ILP
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += IB) {
+        float acc[IB];
+#pragma unroll
+        for (int u = 0; u < IB; ++u) acc[u] = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int u = 0; u < IB; ++u) acc[u] = fmaf(tap_d<N>((i0 + u - j) & (N - 1)), x[j], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < IB; ++u) o[i0 + u] = acc[u];
+    }
+}
+
+// y[i] = sum_m g[(2i - m) mod 2N] a[m]
+template <int N>
+__device__ __forceinline__ void down_line(const float (&a)[2 * N], float (&y)[N]) {
+    constexpr int IB = N >= 4 ? 4 : N;
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += IB) {
+        float acc[IB];
+#pragma unroll
+        for (int u = 0; u < IB; ++u) acc[u] = 0.f;
+#pragma unroll
+        for (int m = 0; m < 2 * N; ++m) {
+#pragma unroll
+            for (int u = 0; u < IB; ++u)
+                acc[u] = fmaf(tap_g<N>((2 * (i0 + u) - m) & (2 * N - 1)), a[m], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < IB; ++u) y[i0 + u] = acc[u];
+    }
+}
+
+template <int N, int CG>
+struct Tile {
+    static constexpr int PITCH = (2 * N + 1) * CG;  // floats per tile row (padded)
+    static constexpr int SMEM_BYTES = N * PITCH * 4;
+};
+
+// N: side of the SMALL plane (input of FACT / UP2, output of DOWN2).
+template <int N, int CG, int MODE, int ACT>
+__global__ void __launch_bounds__(256, 2)
+resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
+                const float* __restrict__ scale, const float* __restrict__ shift) {
+    extern __shared__ float tile[];
+    constexpr int PITCH = Tile<N, CG>::PITCH;
+    constexpr int M = 2 * N;
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * CG;
+
+    if constexpr (MODE != MODE_DOWN2) {
+        // pass 1: rows
+        for (int t = threadIdx.x; t < N * CG; t += blockDim.x) {
+            const int c = t % CG, i = t / CG;
+            float sc = 1.f, sh = 0.f;
+            if (scale != nullptr) {
+                sc = scale[(size_t)b * C + c0 + c];
+                sh = shift[(size_t)b * C + c0 + c];
+            }
+            const float* xp = x + ((size_t)(b * N + i) * N) * C + c0 + c;
+            float xr[N], od[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) xr[j] = fmaf(xp[(size_t)j * C], sc, sh);
+            up_odd<N>(xr, od);
+            float* row = tile + i * PITCH + c;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                row[(2 * j) * CG] = xr[j];
+                row[(2 * j + 1) * CG] = od[j];
+            }
+        }
+        __syncthreads();
+    }
+
+    // pass 2 (+3): columns
+    for (int t = threadIdx.x; t < M * CG; t += blockDim.x) {
+        const int c = t % CG, jj = t / CG;
+        float a[M];
+        if constexpr (MODE != MODE_DOWN2) {
+            float col[N], od[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) col[i] = tile[i * PITCH + jj * CG + c];
+            up_odd<N>(col, od);
+            if constexpr (MODE == MODE_UP2) {
+                float* yp = y + ((size_t)(b * M) * M + jj) * C + c0 + c;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    yp[(size_t)(2 * i) * M * C] = apply_act<ACT>(col[i]);
+                    yp[(size_t)(2 * i + 1) * M * C] = apply_act<ACT>(od[i]);
+                }
+                continue;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    a[2 * i] = apply_act<ACT>(col[i]);
+                    a[2 * i + 1] = apply_act<ACT>(od[i]);
+                }
+            }
+        } else {
+            const float* xp = x + ((size_t)(b * M) * M + jj) * C + c0 + c;
+#pragma unroll
+            for (int m = 0; m < M; ++m) a[m] = xp[(size_t)m * M * C];
+        }
+        float yl[N];
+        down_line<N>(a, yl);
+#pragma unroll
+        for (int i = 0; i < N; ++i) tile[i * PITCH + jj * CG + c] = yl[i];
+    }
+    if constexpr (MODE == MODE_UP2) return;
+    __syncthreads();
+
+    // pass 4: rows
+    for (int t = threadIdx.x; t < N * CG; t += blockDim.x) {
+        const int c = t % CG, i = t / CG;
+        float a[M], yl[N];
+        const float* row = tile + i * PITCH + c;
+#pragma unroll
+        for (int m = 0; m < M; ++m) a[m] = row[m * CG];
+        down_line<N>(a, yl);
+        float* yp = y + ((size_t)(b * N + i) * N) * C + c0 + c;
+#pragma unroll
+        for (int j = 0; j < N; ++j) yp[(size_t)j * C] = yl[j];
+    }
+}
+
+template <int N, int CG, int MODE, int ACT>
+int launch_one(const float* x, float* y, int B, int C, const float* scale, const float* shift,
+               cudaStream_t st) {
+    if (C % CG != 0) return AFLDM_E_SHAPE;
+    auto kern = resample_kernel<N, CG, MODE, ACT>;
+    constexpr int smem = Tile<N, CG>::SMEM_BYTES;
+    static bool configured = false;  // attribute is per-function, set once (idempotent)
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    constexpr int tasks = 2 * N * CG;
+    const int threads = tasks >= 256 ? 256 : (tasks < 32 ? 32 : tasks);
+    kern<<<dim3(C / CG, B), threads, smem, st>>>(x, y, C, scale, shift);
+    return launched();
+}
+
+template <int MODE, int ACT>
+int dispatch_n(const float* x, float* y, int B, int n, int C, const float* scale, const float* shift,
+               cudaStream_t st) {
+    switch (n) {
+        case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
+        case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
+        case 8: return launch_one<8, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
+        case 16: return launch_one<16, 16, MODE, ACT>(x, y, B, C, scale, shift, st);
+        case 32: return launch_one<32, 8, MODE, ACT>(x, y, B, C, scale, shift, st);
+        default: return AFLDM_E_NOKERNEL;
+    }
+}
+
+bool bad_args(const float* x, const float* y, int B, int H, int W, int C, const float* scale,
+              const float* shift) {
+    return x == nullptr || y == nullptr || B <= 0 || H <= 0 || W <= 0 || C <= 0 ||
+           ((scale == nullptr) != (shift == nullptr));
+}
+
+}  // namespace
+}  // namespace afldm
+
+using namespace afldm;
+
+extern "C" int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int W, int C, int act,
+                                      const float* scale, const float* shift, afldm_stream_t stream) {
+    if (bad_args(x, y, B, H, W, C, scale, shift)) return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;  // the reference's mask is built from W only (ideal_lpf.py:81-88)
+    cudaStream_t st = as_stream(stream);
+    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, scale, shift, st);
+    if (act == AFLDM_ACT_IDENTITY)
+        return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
+    return AFLDM_E_ARG;
+}
+
+extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
+                                   const float* scale, const float* shift, afldm_stream_t stream) {
+    if (bad_args(x, y, B, H, W, C, scale, shift) || x == y) return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;
+    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, as_stream(stream));
+}
+
+extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C,
+                                   afldm_stream_t stream) {
+    if (bad_args(x, y, B, H, W, C, nullptr, nullptr) || x == y) return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;
+    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, nullptr, nullptr, as_stream(stream));
+}

@@ -1,0 +1,157 @@
+/*
+ * afldm_b200 - C ABI of the B200-native (sm_100a) AF-LDM denoising hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream, never allocates,
+ * keeps no mutable global device state (graph-capturable, one process per GPU), and returns
+ *      0            success
+ *      < 0          AFLDM_E_* : argument/shape not supported (nothing was launched)
+ *      > 0          a cudaError_t from the launch
+ * Activations are fp32, channels-last ("NHWC": [B][H][W][C], C contiguous) unless a function
+ * says NCHW.  This is the layout torch calls `channels_last`, so the reference's NCHW-shaped
+ * tensors map onto it without a copy.
+ *
+ * Each function cites the reference interface it replaces (paths relative to /root/reference).
+ * The reference attaches native code through torch-extension plugins
+ * (afldm/af_libs/torch_utils/custom_ops.py:59-155, ops/upfirdn2d.cpp:16,102-105); the binding a
+ * maintainer would add on the reference side is the ctypes stub shown in INTEGRATION.md.
+ */
+#ifndef AFLDM_B200_H
+#define AFLDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AFLDM_API __attribute__((visibility("default")))
+#else
+#define AFLDM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* afldm_stream_t; /* cudaStream_t */
+
+enum {
+    AFLDM_OK = 0,
+    AFLDM_E_SHAPE = -1,    /* size / divisibility not supported by the kernel family     */
+    AFLDM_E_ARG = -2,      /* null pointer, bad enum, misaligned pointer                 */
+    AFLDM_E_NOKERNEL = -3, /* no specialisation for this size (cf. filtered_lrelu.cpp:52) */
+    AFLDM_E_WORKSPACE = -4 /* caller scratch too small                                    */
+};
+
+enum { AFLDM_ACT_IDENTITY = 0, AFLDM_ACT_SILU = 1 };
+enum { AFLDM_CONV_SIMT_F32 = 0, AFLDM_CONV_TCGEN05_TF32 = 1 };
+
+/* Library / build identification. abi = 1. */
+AFLDM_API int afldm_abi_version(void);
+/* Number of kernels this library has launched since load (host-side counter, for bench.py). */
+AFLDM_API unsigned long long afldm_launch_count(void);
+/* Human-readable text for a return code of this library (negative) or of CUDA (positive). */
+AFLDM_API const char* afldm_error_string(int code);
+
+/* ---- ideal resampling ----------------------------------------------------------------------
+ * For a circular signal of even length n the reference's FFT filters are circulant:
+ *   UpsampleRFFT(2):   y[2i] = x[i],  y[2i+1] = sum_j d[(i-j) mod n] x[j]
+ *   LPF_RFFT(.5)[::2]: y[i]  = sum_m g[(2i-m) mod 2n] x[m]            (x has length 2n)
+ * (afldm/af_libs/ideal_lpf.py:12-49 masks, :69-93, :112-134, :148-158).  The taps d, g are
+ * baked into the library for n in {2,4,8,16,32,64,128} (afldm_b200/csrc/gen_taps.py).
+ * Planes must be square (the reference builds its mask from the last dim only,
+ * ideal_lpf.py:81-88) and C a multiple of 32. */
+
+/* WarpedNonlinearity.forward (afldm/af_modules/af_blocks.py:19-28) for 4-D input:
+ *   y = LPF(act(Up2(x * scale + shift)))[::2, ::2]   per (b, c) plane,
+ * scale/shift are optional per-(b,c) vectors [B*C] (GroupNorm folded in: scale = gamma*rstd,
+ * shift = beta - mean*gamma*rstd); pass NULL for none.  x, y: NHWC [B,H,W,C]; may alias. */
+AFLDM_API int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int W, int C, int act,
+                           const float* scale, const float* shift, afldm_stream_t stream);
+
+/* UpsampleRFFT(up=2).forward (afldm/af_libs/ideal_lpf.py:148-158), optional affine on load:
+ * x NHWC [B,H,W,C] -> y NHWC [B,2H,2W,C]. */
+AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
+                        const float* scale, const float* shift, afldm_stream_t stream);
+
+/* LPF_RFFT(0.5)(x)[:, :, ::2, ::2] (afldm/af_modules/af_blocks.py:149-150):
+ * x NHWC [B,2H,2W,C] -> y NHWC [B,H,W,C]  (H, W are the OUTPUT sizes). */
+AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, afldm_stream_t stream);
+
+/* ---- GroupNorm ----------------------------------------------------------------------------
+ * torch.nn.GroupNorm(groups, C, eps) as used by diffusers ResnetBlock2D / Attention
+ * (SURVEY.md 8a-R).  Produces the folded per-(b,c) affine  y = x*scale + shift :
+ *   scale[b,c] = gamma[c]*rstd[b,g],  shift[b,c] = beta[c] - mean[b,g]*gamma[c]*rstd[b,g].
+ * x NHWC [B,HW,C].  `partial` is caller scratch of afldm_groupnorm_scratch_floats(B,HW,C) floats. */
+AFLDM_API size_t afldm_groupnorm_scratch_floats(int B, int HW, int C);
+AFLDM_API int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, int groups, float eps,
+                               const float* gamma, const float* beta,
+                               float* scale, float* shift, float* partial, afldm_stream_t stream);
+
+/* y = act(x*scale[b,c] + shift[b,c]); x, y NHWC [B,HW,C] (plain nn.SiLU after a norm: UNet tail
+ * conv_norm_out/conv_act, VAE blocks with up_filtered_act=false; act = identity gives the
+ * normalised input of an attention block). scale/shift may be NULL. x may alias y. */
+AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,
+                         const float* scale, const float* shift, afldm_stream_t stream);
+
+/* ---- convolution / linear as implicit GEMM -----------------------------------------------
+ * nn.Conv2d(Cin, Cout, k, stride=1, padding=k/2) with k in {1,3} on NHWC input, fused epilogue:
+ *   y[b,h,w,:] = conv(x)[b,h,w,:] + bias + row_add[b,:] + residual[b,h,w,:]
+ * (diffusers ResnetBlock2D conv1/conv2/conv_shortcut, Up/Downsample2D.conv with the stride
+ *  forced to 1 by af_blocks.py:129, Attention to_q/to_k/to_v/to_out as k = 1).
+ * x has row pitch x_pitch floats per pixel (>= Cin); w is PACKED [Cout][k*k][Cin] (tap-major,
+ * Cin contiguous); bias [Cout] | NULL, row_add [B][Cout] | NULL (time-embedding projection),
+ * residual NHWC with row pitch res_pitch | NULL (may alias y).  y has row pitch y_pitch
+ * (>= Cout) so an output can be written straight into a channel slice of a concat buffer.
+ * algo: AFLDM_CONV_SIMT_F32 = fp32 FMA (exact-fp32 class; any Cin/Cout),
+ *       AFLDM_CONV_TCGEN05_TF32 = tcgen05 tensor cores, TF32 operands, fp32 accumulate in TMEM
+ *       (same numeric class as the reference's default cuDNN path; falls back to
+ *       AFLDM_E_NOKERNEL when the shape does not fit: Cin % 32, Cout % 16, W power of two).
+ * workspace: split-K partial sums, afldm_conv2d_workspace_floats(...) floats (may be 0). */
+AFLDM_API size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
+AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
+                     const float* row_add, const float* residual, int res_pitch,
+                     float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
+                     int algo, float* workspace, size_t workspace_floats, afldm_stream_t stream);
+
+/* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
+ * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */
+AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float* bias, float* y,
+                          int M, int K, int N, int act_in, int act_out, afldm_stream_t stream);
+
+/* ---- attention ----------------------------------------------------------------------------
+ * F.scaled_dot_product_attention(q,k,v) of diffusers AttnProcessor2_0 with the
+ * cross-frame K/V source of afldm/pipelines/cross_frame_attn.py:79-97:
+ *   q [B][Nq][heads*d] (row pitch q_pitch), k/v [Bkv][Nk][heads*d] (row pitch kv_pitch),
+ *   batch b reads K/V batch  b / (B / Bkv)  (repeat semantics of :91-97), scale = d^-0.5,
+ *   o [B][Nq][heads*d] (row pitch o_pitch).  d % 4 == 0, d <= 64 in this build. */
+AFLDM_API int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
+                        float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                        afldm_stream_t stream);
+
+/* ---- small ops of one denoising step --------------------------------------------------------
+ * diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t f_k) | sin(t f_k)],
+ * f_k = exp(-ln(10000) k / (dim/2)). */
+AFLDM_API int afldm_timestep_embedding_f32(const float* t, float* out, int B, int dim, afldm_stream_t stream);
+/* torch.cat([a, b], dim=1) on NHWC: y[.., :Ca] = a, y[.., Ca:] = b (UNet up-path skip concat). */
+AFLDM_API int afldm_concat_channels_f32(const float* a, int Ca, const float* b, int Cb, float* y,
+                              long long pixels, afldm_stream_t stream);
+/* NCHW [B,C,H,W] <-> NHWC [B,H,W,C] (pipeline boundary: latents / decoded frames). */
+AFLDM_API int afldm_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream);
+AFLDM_API int afldm_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream);
+/* DDIMScheduler.step with eta = 0 (afldm/pipelines/ldm_pipeline.py:103-109):
+ *   x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t);  out = sqrt(a_p) x0 + sqrt(1-a_p) eps
+ * passed as the two host-computed coefficients  out = cx*x + ce*eps.  out may alias x. */
+AFLDM_API int afldm_axpby_f32(const float* x, const float* eps, float* out, float cx, float ce, long long n,
+                    afldm_stream_t stream);
+
+/* ---- StyleGAN3 upfirdn2d (afldm/af_libs/torch_utils/ops/upfirdn2d.cpp:16; BASELINE config #1)
+ * x NCHW [B,C,H,W] contiguous, f [fh][fw] (2-D, already normalised; gain applied here),
+ * y NCHW [B,C,outH,outW], outW = (W*upx + padx0 + padx1 - fw + downx)/downx (upfirdn2d.cpp:35). */
+AFLDM_API int afldm_upfirdn2d_f32(const float* x, const float* f, float* y, int B, int C, int H, int W,
+                        int fh, int fw, int upx, int upy, int downx, int downy,
+                        int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                        afldm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFLDM_B200_H */
