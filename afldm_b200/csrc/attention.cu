@@ -117,6 +117,28 @@ attention_kernel(const float* __restrict__ q, int q_pitch, const float* __restri
     }
 }
 
+// x[r][:] = softmax(scale * x[r][:]); one warp per row, row kept in registers when cols <= 1024.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ x, long long rows, int cols, int pitch, float scale_log2e) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float* xr = x + row * pitch;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c] * scale_log2e);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+        const float p = exp2f(xr[c] * scale_log2e - mx);
+        xr[c] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int c = lane; c < cols; c += 32) xr[c] *= inv;
+}
+
 template <int D>
 int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
            int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
@@ -131,6 +153,16 @@ int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_p
 }  // namespace afldm
 
 using namespace afldm;
+
+extern "C" int afldm_softmax_rows_f32(float* x, long long rows, int cols, int pitch, float scale,
+                                      afldm_stream_t stream) {
+    if (x == nullptr || rows <= 0 || cols <= 0 || pitch < cols) return AFLDM_E_ARG;
+    const long long blocks = (rows + 7) / 8;
+    if (blocks > 0x7fffffffLL) return AFLDM_E_SHAPE;
+    softmax_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, rows, cols, pitch,
+                                                                         scale * 1.4426950408889634f);
+    return launched();
+}
 
 extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
                                    float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,

@@ -6,12 +6,14 @@ using namespace afldm;
 
 namespace {
 bool conv_bad_args(const float* x, int x_pitch, const float* w, const float* y, int y_pitch,
+                   const float* row_add, int row_add_pitch,
                    const float* residual, int res_pitch, int B, int H, int W, int Cin, int Cout, int ks) {
     if (x == nullptr || w == nullptr || y == nullptr) return true;
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return true;
     if (ks != 1 && ks != 3) return true;
     if (x_pitch < Cin || y_pitch < Cout) return true;
     if (residual != nullptr && res_pitch < Cout) return true;
+    if (row_add != nullptr && row_add_pitch < Cout) return true;
     if (x == y) return true;
     return false;
 }
@@ -29,17 +31,17 @@ extern "C" size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, in
 }
 
 extern "C" int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
-                                const float* row_add, const float* residual, int res_pitch, float* y,
+                                const float* row_add, int row_add_pitch, const float* residual, int res_pitch, float* y,
                                 int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize, int algo,
                                 float* workspace, size_t workspace_floats, afldm_stream_t stream) {
-    if (conv_bad_args(x, x_pitch, w, y, y_pitch, residual, res_pitch, B, H, W, Cin, Cout, ksize))
+    if (conv_bad_args(x, x_pitch, w, y, y_pitch, row_add, row_add_pitch, residual, res_pitch, B, H, W, Cin, Cout, ksize))
         return AFLDM_E_ARG;
     cudaStream_t st = as_stream(stream);
     if (algo == AFLDM_CONV_SIMT_F32)
-        return conv_simt_launch(x, x_pitch, w, bias, row_add, residual, res_pitch, y, y_pitch, B, H, W, Cin,
+        return conv_simt_launch(x, x_pitch, w, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Cin,
                                 Cout, ksize, workspace, workspace_floats, st);
     if (algo == AFLDM_CONV_TCGEN05_TF32)
-        return conv_tc_launch(x, x_pitch, w, bias, row_add, residual, res_pitch, y, y_pitch, B, H, W, Cin,
+        return conv_tc_launch(x, x_pitch, w, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Cin,
                               Cout, ksize, workspace, workspace_floats, st);
     return AFLDM_E_ARG;
 }

@@ -50,7 +50,7 @@ struct ConvArgs {
     const float* residual;
     float* y;
     float* ws;
-    int x_pitch, res_pitch, y_pitch;
+    int x_pitch, res_pitch, y_pitch, row_add_pitch;
     int B, H, W, Cin, Cout, ks, M, K, chunks_per_split, kchunks;
 };
 
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
                 if (n + j >= a.Cout) continue;
                 float v = acc[i][j];
                 if (a.bias != nullptr) v += a.bias[n + j];
-                if (a.row_add != nullptr) v += a.row_add[(size_t)b * a.Cout + n + j];
+                if (a.row_add != nullptr) v += a.row_add[(size_t)b * a.row_add_pitch + n + j];
                 if (a.residual != nullptr) v += a.residual[(size_t)m * a.res_pitch + n + j];
                 a.y[(size_t)m * a.y_pitch + n + j] = v;
             }
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
 // Shared with the tensor-core path: y = sum_z ws[z] + bias + row_add + residual.
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splitk, const float* __restrict__ bias,
-                     const float* __restrict__ row_add, const float* residual, int res_pitch,
-                     float* y, int y_pitch, int M, int Cout, int HW) {
+                     const float* __restrict__ row_add, int row_add_pitch, const float* residual,
+                     int res_pitch, float* y, int y_pitch, int M, int Cout, int HW) {
     const long long total = (long long)M * Cout;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -209,7 +209,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splitk, const float* __re
         float v = 0.f;
         for (int z = 0; z < splitk; ++z) v += ws[(size_t)z * total + i];
         if (bias != nullptr) v += bias[n];
-        if (row_add != nullptr) v += row_add[(size_t)(m / HW) * Cout + n];
+        if (row_add != nullptr) v += row_add[(size_t)(m / HW) * row_add_pitch + n];
         if (residual != nullptr) v += residual[(size_t)m * res_pitch + n];
         y[(size_t)m * y_pitch + n] = v;
     }
@@ -218,16 +218,17 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splitk, const float* __re
 }  // namespace
 
 void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const float* row_add,
-                          const float* residual, int res_pitch, float* y, int y_pitch, int M, int Cout,
+                          int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int M, int Cout,
                           int HW, cudaStream_t st) {
     const long long total = (long long)M * Cout;
     const int blocks = (int)std::min<long long>(148 * 4, (total + 255) / 256);
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splitk, bias, row_add, residual, res_pitch, y, y_pitch,
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splitk, bias, row_add, row_add_pitch, residual, res_pitch, y,
+                                                 y_pitch,
                                                  M, Cout, HW);
 }
 
 int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* bias,
-                     const float* row_add, const float* residual, int res_pitch, float* y,
+                     const float* row_add, int row_add_pitch, const float* residual, int res_pitch, float* y,
                      int y_pitch, int B, int H, int W, int Cin, int Cout, int ks, float* workspace,
                      size_t workspace_floats, cudaStream_t st) {
     const ConvPlan p = conv_simt_plan(B, H, W, Cin, Cout, ks);
@@ -236,7 +237,7 @@ int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* b
     ConvArgs a;
     a.x = x; a.w = w; a.bias = bias; a.row_add = row_add; a.residual = residual; a.y = y;
     a.ws = workspace;
-    a.x_pitch = x_pitch; a.res_pitch = res_pitch; a.y_pitch = y_pitch;
+    a.x_pitch = x_pitch; a.res_pitch = res_pitch; a.y_pitch = y_pitch; a.row_add_pitch = row_add_pitch;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ks; a.M = p.M; a.K = p.K;
     a.chunks_per_split = p.chunks_per_split; a.kchunks = p.kchunks;
     const bool fast = (Cin % 16 == 0) && (x_pitch % 4 == 0) && aligned16(x) && aligned16(w);
@@ -247,7 +248,7 @@ int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* b
         conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);
     int launches = 1;
     if (p.splitk > 1) {
-        splitk_reduce_launch(workspace, p.splitk, bias, row_add, residual, res_pitch, y, y_pitch, p.M, Cout,
+        splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, p.M, Cout,
                              H * W, st);
         ++launches;
     }

@@ -7,7 +7,7 @@ namespace afldm {
 
 bool conv_tc_workspace_floats(int, int, int, int, int, int, size_t*) { return false; }
 
-int conv_tc_launch(const float*, int, const float*, const float*, const float*, const float*, int, float*,
+int conv_tc_launch(const float*, int, const float*, const float*, const float*, int, const float*, int, float*,
                    int, int, int, int, int, int, int, float*, size_t, cudaStream_t) {
     return AFLDM_E_NOKERNEL;
 }

@@ -104,6 +104,15 @@ axpby_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __
         out[i] = fmaf(cx, x[i], ce * e[i]);
 }
 
+__global__ void __launch_bounds__(256)
+axpby_dev_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out,
+                 const float* __restrict__ coef, long long n) {
+    const float cx = coef[0], ce = coef[1];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fmaf(cx, x[i], ce * e[i]);
+}
+
 // ------------------------------------------------------------------ upfirdn2d (NCHW)
 // out[oy][ox] = gain * sum_{fy,fx} f'[fy][fx] * xup[oy*downy + fy - pady0][ox*downx + fx - padx0]
 // where xup is x zero-stuffed by (upy, upx) and f' = f flipped unless `flip`
@@ -213,6 +222,13 @@ extern "C" int afldm_axpby_f32(const float* x, const float* eps, float* out, flo
                                afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || n <= 0) return AFLDM_E_ARG;
     axpby_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, eps, out, cx, ce, n);
+    return launched();
+}
+
+extern "C" int afldm_axpby_dev_f32(const float* x, const float* eps, float* out, const float* coef,
+                                   long long n, afldm_stream_t stream) {
+    if (x == nullptr || eps == nullptr || out == nullptr || coef == nullptr || n <= 0) return AFLDM_E_ARG;
+    axpby_dev_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, eps, out, coef, n);
     return launched();
 }
 

@@ -1,0 +1,2 @@
+from .unet_2d import UNet2DModel  # noqa: F401
+from .af_vae import AliasFreeAutoencoderKL, AutoencoderKL  # noqa: F401

@@ -1,0 +1,289 @@
+"""Host-side mirror of the diffusers 0.32.1 building blocks the reference mutates, with forwards
+that launch the sm_100a kernels (call sites in the reference:
+afldm/af_modules/af_api.py:9-31, afldm/pipelines/cross_frame_attn.py:54-130).
+
+Parameter names / shapes are the diffusers ones (``norm1, conv1, time_emb_proj, norm2, conv2,
+conv_shortcut``; ``group_norm, to_q, to_k, to_v, to_out.0``; ``downsamplers.0.conv``;
+``upsamplers.0.conv``) so a diffusers checkpoint's ``state_dict`` loads unchanged.  ``nn.Conv2d`` /
+``nn.GroupNorm`` / ``nn.Linear`` objects are used as parameter containers only; their own
+``forward`` is never called on the hot path.
+
+Tensors between modules are logical [B,C,H,W], physically channels_last (NHWC).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..af_modules.af_blocks import WarpedNonlinearity, act_name
+from ..packing import conv_params, fused_linear_params
+
+
+def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module) -> torch.Tensor:
+    """act(GroupNorm(x)) on NHWC x: statistics pass + one fused apply kernel.
+    A ``WarpedNonlinearity`` (alias-free surgery) selects the filtered activation."""
+    scale, shift = ops.groupnorm_affine(x, norm.num_groups, norm.eps, norm.weight, norm.bias)
+    if isinstance(nonlinearity, WarpedNonlinearity):
+        return ops.filtered_act(x, scale, shift, act=nonlinearity.act)
+    return ops.affine_act(x, scale, shift, act=act_name(nonlinearity))
+
+
+class ResnetBlock2D(nn.Module):
+    """diffusers ResnetBlock2D ("default" time-scale-shift, output_scale_factor 1, no dropout)."""
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int],
+                 groups: int = 32, eps: float = 1e-5):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels else None
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
+        self.nonlinearity = nn.SiLU()       # the one shared activation that make_af_* wraps
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+    def forward(self, input_tensor: torch.Tensor, temb: Optional[torch.Tensor] = None,
+                temb_proj: Optional[torch.Tensor] = None, *args, **kwargs) -> torch.Tensor:
+        """``temb`` [B, temb_channels]; ``temb_proj`` = precomputed time_emb_proj(act(temb)) [B, Cout]
+        (the UNet batches these for all its resnets into one launch)."""
+        x = ops.nhwc(input_tensor)
+        if temb_proj is None and temb is not None and self.time_emb_proj is not None:
+            temb_proj = ops.linear_rows(temb.contiguous(), self.time_emb_proj.weight, self.time_emb_proj.bias,
+                                        act_in="silu")
+        w1, b1, k1 = conv_params(self.conv1)
+        h = ops.conv2d(norm_act(x, self.norm1, self.nonlinearity), w1, b1, k1, row_add=temb_proj)
+        a = norm_act(h, self.norm2, self.nonlinearity)
+        w2, b2, k2 = conv_params(self.conv2)
+        if self.conv_shortcut is not None:
+            ws, bs, ks = conv_params(self.conv_shortcut)
+            sc = ops.conv2d(x, ws, bs, ks)
+            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc)
+        else:
+            out = ops.conv2d(a, w2, b2, k2, residual=x)
+        return ops.nchw_view(out)
+
+
+class AttnProcessor2_0:
+    """diffusers AttnProcessor2_0 for the attention-block form (4-D input), CUDA kernels inside.
+
+    ``encoder_hidden_states`` ([Bkv, Nk, C], already normalised by the caller, as in
+    cross_frame_attn.py:86-97) supplies K/V; Bkv may divide B (each K/V batch serves B/Bkv queries
+    batches without being tiled in memory)."""
+
+    def __call__(self, attn: "Attention", hidden_states: torch.Tensor,
+                 encoder_hidden_states: Optional[torch.Tensor] = None, attention_mask=None, temb=None,
+                 *args, **kwargs) -> torch.Tensor:
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is not used on the AF-LDM path")
+        x = ops.nhwc(hidden_states)
+        b, h, w, c = x.shape
+        xn = x
+        if attn.group_norm is not None:
+            gn = attn.group_norm
+            scale, shift = ops.groupnorm_affine(x, gn.num_groups, gn.eps, gn.weight, gn.bias)
+            xn = ops.affine_act(x, scale, shift, act="identity")
+        if encoder_hidden_states is None:
+            wqkv, bqkv = fused_linear_params(attn, "qkv", (attn.to_q, attn.to_k, attn.to_v))
+            qkv = ops.conv2d(xn, wqkv, bqkv, 1).view(b, h * w, 3 * c)
+            q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
+        else:
+            src = encoder_hidden_states
+            if src.ndim != 3 or src.shape[-1] != c:
+                raise ValueError("encoder_hidden_states must be [Bkv, Nk, C]")
+            src = src.contiguous()
+            wq, bq, _ = conv_params(attn.to_q)
+            q = ops.conv2d(xn, wq, bq, 1).view(b, h * w, c)
+            wkv, bkv = fused_linear_params(attn, "kv", (attn.to_k, attn.to_v))
+            kv = ops.conv2d(src.view(src.shape[0], src.shape[1], 1, c), wkv, bkv, 1).view(src.shape[0], src.shape[1], 2 * c)
+            k, v = kv[:, :, :c], kv[:, :, c:]
+        d = c // attn.heads
+        if d <= 64 and d % 8 == 0:
+            o = ops.attention(q, k, v, attn.heads)
+        else:
+            o = ops.attention_gemm(q, k, v, attn.heads)
+        wo, bo, _ = conv_params(attn.to_out[0])
+        out = ops.conv2d(o.view(b, h, w, c), wo, bo, 1, residual=x if attn.residual_connection else None)
+        if attn.rescale_output_factor != 1.0:
+            raise NotImplementedError("rescale_output_factor != 1")
+        return ops.nchw_view(out)
+
+
+class Attention(nn.Module):
+    """diffusers Attention in its attention-block configuration (bias, group norm, residual)."""
+
+    def __init__(self, channels: int, heads: int, dim_head: int, groups: int = 32, eps: float = 1e-5):
+        super().__init__()
+        if heads * dim_head != channels:
+            raise ValueError("heads * dim_head must equal channels")
+        self.heads, self.dim_head = heads, dim_head
+        self.scale = dim_head ** -0.5
+        self.residual_connection = True
+        self.rescale_output_factor = 1.0
+        self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
+        self.to_q = nn.Linear(channels, channels)
+        self.to_k = nn.Linear(channels, channels)
+        self.to_v = nn.Linear(channels, channels)
+        self.to_out = nn.ModuleList([nn.Linear(channels, channels), nn.Dropout(0.0)])
+        self.processor = AttnProcessor2_0()
+
+    def set_processor(self, processor) -> None:
+        self.processor = processor
+
+    def get_processor(self):
+        return self.processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, **kwargs):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states, **kwargs)
+
+
+class Downsample2D(nn.Module):
+    """diffusers Downsample2D (3x3 conv, stride 2).  Holds the weights that
+    ``replace_downsampler`` hands to ``AliasFreeDownsample2D``; the aliasing original itself has
+    no kernel in this build."""
+
+    def __init__(self, channels: int, use_conv: bool = True, out_channels: Optional[int] = None,
+                 padding: int = 1, name: str = "op"):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.use_conv, self.padding, self.name = use_conv, padding, name
+        self.norm = None
+        self.conv = nn.Conv2d(channels, self.out_channels, 3, stride=2, padding=padding)
+
+    def forward(self, hidden_states, *args, **kwargs):
+        raise NotImplementedError("plain (aliasing) Downsample2D: call make_af_unet / make_af_vae first")
+
+
+class Upsample2D(nn.Module):
+    """diffusers Upsample2D (nearest x2 + 3x3 conv); see ``Downsample2D``."""
+
+    def __init__(self, channels: int, use_conv: bool = True, out_channels: Optional[int] = None,
+                 name: str = "conv"):
+        super().__init__()
+        self.channels, self.out_channels = channels, out_channels or channels
+        self.use_conv, self.name = use_conv, name
+        self.use_conv_transpose = False
+        self.norm = None
+        self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=1)
+
+    def forward(self, hidden_states, output_size=None, *args, **kwargs):
+        raise NotImplementedError("plain (aliasing) Upsample2D: call make_af_unet / make_af_vae first")
+
+
+# --------------------------------------------------------------------------------- UNet blocks
+class DownBlock2D(nn.Module):
+    """DownBlock2D / AttnDownBlock2D (``attention_head_dim`` None = no attention)."""
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers, add_downsample,
+                 attention_head_dim, eps, downsample_padding=1):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D(in_channels if i == 0 else out_channels, out_channels, temb_channels, eps=eps)
+            for i in range(num_layers)])
+        self.attentions = None
+        if attention_head_dim:
+            self.attentions = nn.ModuleList([
+                Attention(out_channels, out_channels // attention_head_dim, attention_head_dim, eps=eps)
+                for _ in range(num_layers)])
+        self.downsamplers = None
+        if add_downsample:
+            self.downsamplers = nn.ModuleList(
+                [Downsample2D(out_channels, True, out_channels, padding=downsample_padding, name="op")])
+
+    def forward(self, hidden_states, temb=None, temb_projs=None):
+        outputs = ()
+        for i, resnet in enumerate(self.resnets):
+            hidden_states = resnet(hidden_states, temb, None if temb_projs is None else temb_projs[i])
+            if self.attentions is not None:
+                hidden_states = self.attentions[i](hidden_states)
+            outputs += (hidden_states,)
+        if self.downsamplers is not None:
+            hidden_states = self.downsamplers[0](hidden_states)
+            outputs += (hidden_states,)
+        return hidden_states, outputs
+
+
+class UNetMidBlock2D(nn.Module):
+    def __init__(self, channels, temb_channels, attention_head_dim, eps):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(channels, channels, temb_channels, eps=eps),
+                                      ResnetBlock2D(channels, channels, temb_channels, eps=eps)])
+        self.attentions = nn.ModuleList(
+            [Attention(channels, channels // attention_head_dim, attention_head_dim, eps=eps)])
+
+    def forward(self, hidden_states, temb=None, temb_projs=None):
+        tp = temb_projs if temb_projs is not None else (None, None)
+        hidden_states = self.resnets[0](hidden_states, temb, tp[0])
+        hidden_states = self.attentions[0](hidden_states)
+        return self.resnets[1](hidden_states, temb, tp[1])
+
+
+class UpBlock2D(nn.Module):
+    """UpBlock2D / AttnUpBlock2D: each resnet consumes cat([h, skip]) (skip popped from the end)."""
+
+    def __init__(self, in_channels, out_channels, prev_output_channel, temb_channels, num_layers,
+                 add_upsample, attention_head_dim, eps):
+        super().__init__()
+        resnets = []
+        for i in range(num_layers):
+            skip_channels = in_channels if i == num_layers - 1 else out_channels
+            first = prev_output_channel if i == 0 else out_channels
+            resnets.append(ResnetBlock2D(first + skip_channels, out_channels, temb_channels, eps=eps))
+        self.resnets = nn.ModuleList(resnets)
+        self.attentions = None
+        if attention_head_dim:
+            self.attentions = nn.ModuleList([
+                Attention(out_channels, out_channels // attention_head_dim, attention_head_dim, eps=eps)
+                for _ in range(num_layers)])
+        self.upsamplers = None
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([Upsample2D(out_channels, True, out_channels)])
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, temb_projs=None):
+        skips = list(res_hidden_states_tuple)
+        for i, resnet in enumerate(self.resnets):
+            skip = skips.pop()
+            cat = ops.nchw_view(ops.concat_channels(ops.nhwc(hidden_states), ops.nhwc(skip)))
+            hidden_states = resnet(cat, temb, None if temb_projs is None else temb_projs[i])
+            if self.attentions is not None:
+                hidden_states = self.attentions[i](hidden_states)
+        if self.upsamplers is not None:
+            hidden_states = self.upsamplers[0](hidden_states)
+        return hidden_states
+
+
+# --------------------------------------------------------------------------------- VAE blocks
+class UpDecoderBlock2D(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layers, add_upsample, eps=1e-6):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D(in_channels if i == 0 else out_channels, out_channels, None, eps=eps)
+            for i in range(num_layers)])
+        self.upsamplers = nn.ModuleList([Upsample2D(out_channels, True, out_channels)]) if add_upsample else None
+
+    def forward(self, hidden_states, temb=None):
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states, None)
+        if self.upsamplers is not None:
+            hidden_states = self.upsamplers[0](hidden_states)
+        return hidden_states
+
+
+class DownEncoderBlock2D(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layers, add_downsample, eps=1e-6):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            ResnetBlock2D(in_channels if i == 0 else out_channels, out_channels, None, eps=eps)
+            for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList(
+            [Downsample2D(out_channels, True, out_channels, padding=0, name="op")]) if add_downsample else None
+
+    def forward(self, hidden_states):
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states, None)
+        if self.downsamplers is not None:
+            hidden_states = self.downsamplers[0](hidden_states)
+        return hidden_states

@@ -1,0 +1,390 @@
+"""Torch-tensor front end of the C-ABI ops (``include/afldm_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every op below launches
+hand-written sm_100a kernels from ``libafldm_b200.so`` on ``torch.cuda.current_stream()``.
+Activations are fp32 and physically NHWC: functions take / return tensors of shape
+``[B, H, W, C]`` (contiguous).  ``nhwc()`` / ``nchw_view()`` convert from and to the logical
+``[B, C, H, W]`` shape the reference's modules use (free when the tensor is ``channels_last``).
+
+There is no fallback path: on a machine without the library or without a GPU these raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT = {"identity": 0, None: 0, "silu": 1}
+CONV_ALGO = {"simt": 0, "tf32": 1}
+
+_default_conv_algo = "simt"
+
+
+def set_default_conv_algo(name: str) -> None:
+    """'simt' = exact fp32 FMA; 'tf32' = tcgen05 tensor cores (SIMT where a shape does not fit)."""
+    global _default_conv_algo
+    if name not in CONV_ALGO:
+        raise ValueError(name)
+    _default_conv_algo = name
+
+
+def default_conv_algo() -> str:
+    return _default_conv_algo
+
+
+_recorder = None
+
+
+def record_to(records) -> None:
+    """Profiling hook (bench.py): while a list is installed, every op appends
+    ``(name, meta, thunk, keepalive)`` where ``thunk()`` re-issues the identical C call."""
+    global _recorder
+    _recorder = records
+
+
+def _run(name: str, meta: dict, fn, keep=()) -> None:
+    _lib.check(fn(), name)
+    if _recorder is not None:
+        _recorder.append((name, meta, fn, keep))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.AfldmError(f"{name}: afldm_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise _lib.AfldmError(f"{name}: fp32 expected, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.AfldmError(f"{name}: contiguous tensor expected")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------- scratch
+_scratch = {}
+_scratch_retired = []   # outgrown buffers stay alive: captured CUDA graphs may still point at them
+
+
+def scratch(device: torch.device, nfloats: int) -> torch.Tensor:
+    """One grow-only fp32 scratch buffer per device (split-K partials, GroupNorm partials).
+    All ops run on one stream, so consecutive users may share it."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nfloats:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.AfldmError("scratch would grow during CUDA-graph capture: run one eager warm-up first")
+        if buf is not None:
+            _scratch_retired.append(buf)
+        buf = torch.empty(max(nfloats, 1 << 20), dtype=torch.float32, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------- layout
+def nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical [B,C,H,W] -> physical [B,H,W,C] contiguous (zero-copy for channels_last input)."""
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    x = _chk(x.contiguous(), "x")
+    b, c, h, w = x.shape
+    y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("nchw_to_nhwc", dict(elems=x.numel()),
+         lambda: L.afldm_nchw_to_nhwc_f32(x.data_ptr(), y.data_ptr(), b, c, h * w, _stream()), (x, y))
+    return y
+
+
+def nchw_view(y: torch.Tensor) -> torch.Tensor:
+    """Physical [B,H,W,C] -> logical [B,C,H,W] (channels_last strides, zero-copy)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def to_nchw_contiguous(y: torch.Tensor) -> torch.Tensor:
+    """Physical [B,H,W,C] -> contiguous [B,C,H,W] (pipeline boundary)."""
+    _chk(y, "y")
+    b, h, w, c = y.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=y.device)
+    L = _lib.lib()
+    _run("nhwc_to_nchw", dict(elems=y.numel()),
+         lambda: L.afldm_nhwc_to_nchw_f32(y.data_ptr(), out.data_ptr(), b, c, h * w, _stream()), (y, out))
+    return out
+
+
+# ------------------------------------------------------------------------- ideal resampling
+def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                 act: str = "silu", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """WarpedNonlinearity (af_blocks.py:19-28) on NHWC x, optional folded GroupNorm affine."""
+    _chk(x, "x")
+    b, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    L = _lib.lib()
+    _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel()),
+         lambda: L.afldm_filtered_act_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act],
+                                          _ptr(scale), _ptr(shift), _stream()), (x, out, scale, shift))
+    return out
+
+
+def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """UpsampleRFFT(2) (ideal_lpf.py:148-158) on NHWC x."""
+    _chk(x, "x")
+    b, h, w, c = x.shape
+    out = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel()),
+         lambda: L.afldm_up2_ideal_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, _ptr(scale), _ptr(shift),
+                                       _stream()), (x, out, scale, shift))
+    return out
+
+
+def lpf_down2(x: torch.Tensor) -> torch.Tensor:
+    """LPF_RFFT(0.5)(x)[..., ::2, ::2] (af_blocks.py:149-150) on NHWC x."""
+    _chk(x, "x")
+    b, h2, w2, c = x.shape
+    if h2 % 2 or w2 % 2:
+        raise _lib.AfldmError("lpf_down2: even input size expected")
+    out = torch.empty((b, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel()),
+         lambda: L.afldm_lpf_down2_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _stream()), (x, out))
+    return out
+
+
+# ------------------------------------------------------------------------- norm / activation
+def groupnorm_affine(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
+                     beta: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GroupNorm statistics of NHWC x folded into per-(b,c) scale / shift, each [B, C]."""
+    _chk(x, "x")
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    L = _lib.lib()
+    part = scratch(x.device, L.afldm_groupnorm_scratch_floats(b, hw, c))
+    ss = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
+    _run("groupnorm_affine", dict(B=b, HW=hw, C=c, elems=x.numel()),
+         lambda: L.afldm_groupnorm_affine_f32(x.data_ptr(), b, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta),
+                                              ss[0].data_ptr(), ss[1].data_ptr(), part.data_ptr(), _stream()),
+         (x, gamma, beta, ss, part))
+    return ss[0], ss[1]
+
+
+def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+               act: str = "silu", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, "x")
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    if out is None:
+        out = torch.empty_like(x)
+    L = _lib.lib()
+    _run("affine_act", dict(elems=x.numel()),
+         lambda: L.afldm_affine_act_f32(x.data_ptr(), out.data_ptr(), b, hw, c, ACT[act], _ptr(scale), _ptr(shift),
+                                        _stream()), (x, out, scale, shift))
+    return out
+
+
+# ------------------------------------------------------------------------- conv / linear
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d weight [Cout,Cin,kh,kw] (or nn.Linear [Cout,Cin]) -> packed [Cout][kh*kw][Cin]."""
+    if w.ndim == 2:
+        return w.detach().contiguous()
+    co, ci, kh, kw = w.shape
+    return w.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci).contiguous()
+
+
+def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
+           row_add: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, algo: Optional[str] = None) -> torch.Tensor:
+    """Stride-1 'same' convolution (k = 1 or 3) of NHWC x with the fused epilogue
+    ``+ bias + row_add[b] + residual``.  ``x``, ``residual`` and ``out`` may be channel slices of
+    wider NHWC buffers (last-dim stride 1, pixel pitch = stride(-2))."""
+    L = _lib.lib()
+    b, h, w_, cin = x.shape
+    cout = w_packed.shape[0]
+    if x.stride(-1) != 1 or not x.is_cuda or x.dtype != torch.float32:
+        raise _lib.AfldmError("conv2d: fp32 CUDA NHWC tensor expected")
+    x_pitch = _pitch(x)
+    if out is None:
+        out = torch.empty((b, h, w_, cout), dtype=torch.float32, device=x.device)
+    y_pitch = _pitch(out)
+    res_pitch = _pitch(residual) if residual is not None else 0
+    ra_pitch = 0
+    if row_add is not None:
+        if row_add.ndim != 2 or row_add.shape != (b, cout) or row_add.stride(1) != 1:
+            raise _lib.AfldmError("conv2d: row_add must be [B, Cout] with unit column stride")
+        ra_pitch = row_add.stride(0) if b > 1 else cout
+    name = algo or _default_conv_algo
+    meta = dict(B=b, H=h, W=w_, Cin=cin, Cout=cout, k=ksize, flops=2.0 * b * h * w_ * cout * ksize * ksize * cin)
+    keep = (x, w_packed, bias, row_add, residual, out)
+
+    def call(a: int, ws, need: int):
+        return L.afldm_conv2d_f32(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), _ptr(row_add), ra_pitch,
+                                  _ptr(residual), res_pitch, out.data_ptr(), y_pitch, b, h, w_, cin, cout, ksize,
+                                  a, _ptr(ws), need, _stream())
+
+    if CONV_ALGO[name] == 1:
+        need = L.afldm_conv2d_workspace_floats(b, h, w_, cin, cout, ksize, 1)
+        ws = scratch(x.device, need) if need else None
+        code = call(1, ws, need)
+        if code != -3:      # AFLDM_E_NOKERNEL: shape outside the tensor-core family -> exact SIMT kernel
+            _lib.check(code, "conv2d[tf32]")
+            if _recorder is not None:
+                _recorder.append(("conv2d_tf32", meta, lambda: call(1, ws, need), keep + (ws,)))
+            return out
+    need0 = L.afldm_conv2d_workspace_floats(b, h, w_, cin, cout, ksize, 0)
+    ws0 = scratch(x.device, need0) if need0 else None
+    _run("conv2d_simt", meta, lambda: call(0, ws0, need0), keep + (ws0,))
+    return out
+
+
+def _pitch(t: torch.Tensor) -> int:
+    """Pixel pitch (floats) of an NHWC tensor or of a channel slice of a wider NHWC buffer."""
+    b, h, w, c = t.shape
+    if t.stride(3) != 1 and c > 1:
+        raise _lib.AfldmError(f"NHWC tensor with unit channel stride expected, got strides {t.stride()}")
+    p = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if b > 1 else c))
+    ok = p >= c and (w == 1 or t.stride(2) == p) and (h == 1 or t.stride(1) == w * p) and \
+        (b == 1 or t.stride(0) == h * w * p)
+    if not ok:
+        raise _lib.AfldmError(f"unsupported NHWC strides {t.stride()} for shape {tuple(t.shape)}")
+    return p
+
+
+def linear_rows(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act_in: str = "identity",
+                act_out: str = "identity") -> torch.Tensor:
+    """y = act_out(act_in(x) @ w.T + bias) for a few rows (time-embedding MLP)."""
+    _chk(x, "x")
+    _chk(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("linear_rows", dict(M=m, K=k, N=n, bytes=4.0 * n * k),
+         lambda: L.afldm_linear_rows_f32(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), m, k, n,
+                                         ACT[act_in], ACT[act_out], _stream()), (x, w, bias, y))
+    return y
+
+
+# ------------------------------------------------------------------------- attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(d)) v per head.  q [B,Nq,heads*d], k/v [Bkv,Nk,heads*d]; each may be a
+    column slice of a wider (e.g. fused QKV) buffer.  B % Bkv == 0: batch b uses K/V batch b // (B/Bkv)."""
+    b, nq, cd = q.shape
+    bkv, nk, _ = k.shape
+    d = cd // heads
+    for t in (q, k, v):
+        if t.stride(-1) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _lib.AfldmError("attention: rows must be densely pitched")
+    if k.stride(1) != v.stride(1):
+        raise _lib.AfldmError("attention: k and v must share a pitch")
+    if out is None:
+        out = torch.empty((b, nq, cd), dtype=torch.float32, device=q.device)
+    L = _lib.lib()
+    _run("attention", dict(B=b, Nq=nq, Nk=nk, heads=heads, d=d, flops=4.0 * b * heads * nq * nk * d),
+         lambda: L.afldm_attention_f32(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1),
+                                       out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, _stream()),
+         (q, k, v, out))
+    return out
+
+
+def softmax_rows_(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """In-place softmax(scale * x) over the last dim of a contiguous matrix."""
+    _chk(x, "x")
+    cols = x.shape[-1]
+    L = _lib.lib()
+    _run("softmax_rows", dict(elems=x.numel()),
+         lambda: L.afldm_softmax_rows_f32(x.data_ptr(), x.numel() // cols, cols, cols, float(scale), _stream()), (x,))
+    return x
+
+
+def attention_gemm(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """Attention for head dims the register-resident kernel does not cover (VAE mid block: one head
+    of 512): per (batch, head)  S = q k^T  ->  row softmax  ->  O = S v, the two products running
+    through the implicit-GEMM kernel as 1x1 convolutions."""
+    b, nq, cd = q.shape
+    bkv, nk, _ = k.shape
+    d = cd // heads
+    rep = b // bkv
+    out = torch.empty((b, nq, cd), dtype=torch.float32, device=q.device)
+    for bi in range(b):
+        kb = bi // rep
+        for hd in range(heads):
+            sl = slice(hd * d, (hd + 1) * d)
+            qh = q[bi:bi + 1, :, None, sl]                      # [1, Nq, 1, d]  (x of the "conv")
+            kh = k[kb, :, sl].contiguous()                      # [Nk, d]        (weights [Cout=Nk][Cin=d])
+            s = conv2d(qh, kh, None, 1)                         # [1, Nq, 1, Nk]
+            softmax_rows_(s.view(nq, nk), d ** -0.5)
+            vt = to_nchw_contiguous(v[kb:kb + 1, :, None, sl].contiguous()).view(d, nk)   # v^T [d, Nk]
+            conv2d(s, vt, None, 1, out=out[bi:bi + 1, :, None, sl])
+    return out
+
+
+# ------------------------------------------------------------------------- step ops
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    _chk(t, "t")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    L = _lib.lib()
+    _run("timestep_embedding", dict(elems=out.numel()),
+         lambda: L.afldm_timestep_embedding_f32(t.data_ptr(), out.data_ptr(), t.shape[0], dim, _stream()), (t, out))
+    return out
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _chk(a, "a")
+    _chk(b, "b")
+    ca, cb = a.shape[-1], b.shape[-1]
+    pixels = a.numel() // ca
+    y = torch.empty(a.shape[:-1] + (ca + cb,), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    _run("concat_channels", dict(elems=y.numel()),
+         lambda: L.afldm_concat_channels_f32(a.data_ptr(), ca, b.data_ptr(), cb, y.data_ptr(), pixels, _stream()),
+         (a, b, y))
+    return y
+
+
+def axpby(x: torch.Tensor, e: torch.Tensor, cx, ce, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = cx * x + ce * e.  cx/ce floats, or a device tensor ``coef`` of 2 floats passed as cx (ce None)."""
+    _chk(x, "x")
+    _chk(e, "e")
+    if out is None:
+        out = torch.empty_like(x)
+    L = _lib.lib()
+    n = x.numel()
+    if isinstance(cx, torch.Tensor):
+        _run("axpby", dict(elems=n),
+             lambda: L.afldm_axpby_dev_f32(x.data_ptr(), e.data_ptr(), out.data_ptr(), cx.data_ptr(), n, _stream()),
+             (x, e, out, cx))
+    else:
+        fx, fe = float(cx), float(ce)
+        _run("axpby", dict(elems=n),
+             lambda: L.afldm_axpby_f32(x.data_ptr(), e.data_ptr(), out.data_ptr(), fx, fe, n, _stream()), (x, e, out))
+    return out
+
+
+def upfirdn2d(x: torch.Tensor, f: torch.Tensor, up=1, down=1, padding=(0, 0, 0, 0), flip_filter=False,
+              gain=1.0) -> torch.Tensor:
+    """StyleGAN3 upfirdn2d on NCHW x (upfirdn2d.py:118-162); padding = (x0, x1, y0, y1); f 1-D or 2-D."""
+    _chk(x, "x")
+    if f.ndim == 1:
+        f = torch.outer(f, f)
+    f = _chk(f.contiguous(), "f")
+    b, c, h, w = x.shape
+    fh, fw = f.shape
+    px0, px1, py0, py1 = padding
+    ow = (w * up + px0 + px1 - fw + down) // down
+    oh = (h * up + py0 + py1 - fh + down) // down
+    y = torch.empty((b, c, oh, ow), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("upfirdn2d", dict(elems=y.numel()),
+         lambda: L.afldm_upfirdn2d_f32(x.data_ptr(), f.data_ptr(), y.data_ptr(), b, c, h, w, fh, fw, up, up, down, down,
+                                       px0, px1, py0, py1, int(bool(flip_filter)), float(gain), _stream()), (x, f, y))
+    return y

@@ -1,0 +1,50 @@
+"""Weight packing for the implicit-GEMM kernels, cached on the owning nn.Module.
+
+``nn.Conv2d`` keeps its diffusers-compatible ``weight`` [Cout,Cin,kh,kw] / ``bias`` Parameters (so
+checkpoints load unchanged); the kernels read a tap-major copy [Cout][kh*kw][Cin] that is rebuilt
+whenever the Parameter's storage or version changes.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _key(ts: Sequence[Optional[torch.Tensor]]):
+    return tuple(None if t is None else (t.data_ptr(), t._version, str(t.device)) for t in ts)
+
+
+def conv_params(m: nn.Module) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
+    """(packed weight, bias, ksize) of an nn.Conv2d (k in {1,3}) or nn.Linear (as k = 1)."""
+    key = _key((m.weight, m.bias))
+    cache = getattr(m, "_afldm_pack", None)
+    if cache is None or cache[0] != key:
+        w = m.weight
+        if w.ndim == 4:
+            k = w.shape[-1]
+            if w.shape[-2] != k or k not in (1, 3):
+                raise NotImplementedError(f"conv kernel {tuple(w.shape[-2:])} not supported")
+        else:
+            k = 1
+        bias = None if m.bias is None else m.bias.detach().contiguous()
+        cache = (key, (ops.pack_conv_weight(w), bias, k))
+        object.__setattr__(m, "_afldm_pack", cache)
+    return cache[1]
+
+
+def fused_linear_params(owner: nn.Module, tag: str, layers: Sequence[nn.Module]):
+    """Row-concatenated weight / bias of several nn.Linear (or 1x1 conv) layers sharing an input:
+    q|k|v of an attention block, or every resnet's time_emb_proj of a UNet."""
+    key = _key([t for m in layers for t in (m.weight, m.bias)])
+    name = "_afldm_fused_" + tag
+    cache = getattr(owner, name, None)
+    if cache is None or cache[0] != key:
+        w = torch.cat([m.weight.detach().reshape(m.weight.shape[0], -1) for m in layers], dim=0).contiguous()
+        b = torch.cat([m.bias.detach() for m in layers], dim=0).contiguous()
+        cache = (key, (w, b))
+        object.__setattr__(owner, name, cache)
+    return cache[1]

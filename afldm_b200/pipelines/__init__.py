@@ -1,0 +1,2 @@
+from .cross_frame_attn import AttnState, CrossFrameAttnProcessor, get_unet_attn_processors, set_unet_attn_processor  # noqa: F401
+from .ldm_pipeline import MyLDMPipeline  # noqa: F401

@@ -1,0 +1,190 @@
+"""Unconditional latent-diffusion pipeline with the call surface of
+/root/reference/afldm/pipelines/ldm_pipeline.py (``MyLDMPipeline.__call__`` :32-131,
+``ddim_inversion`` :133-160; driven by scripts/shift_ldm_ffhq.py:50-159).
+
+The per-step work (UNet forward + DDIM update) is a fixed sequence of sm_100a kernel launches,
+so it is captured ONCE in a CUDA graph (``GraphedDenoiser``) and replayed for every timestep:
+the timestep and the two DDIM coefficients are read from small device tensors that are refreshed
+between replays, which removes the ~600 launches' worth of host overhead from every step and the
+``t.item()`` synchronisation the reference pays (cross_frame_attn.py:31-33).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Union
+
+import torch
+
+from .. import ops
+from ..af_modules.af_api import make_af_unet
+from ..configs import FFHQ_AFVAE, FFHQ_DDIM, FFHQ_UNET
+from ..models.af_vae import AliasFreeAutoencoderKL
+from ..models.unet_2d import UNet2DModel
+from ..schedulers.ddim import DDIMScheduler
+
+
+class ImagePipelineOutput:
+    def __init__(self, images):
+        self.images = images
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=torch.float32):
+    """diffusers.utils.torch_utils.randn_tensor: sample on the generator's device (CPU by default) so
+    that seeds give the same latents everywhere, then move (ldm_pipeline.py:82-87)."""
+    gdev = generator.device if generator is not None else torch.device("cpu")
+    x = torch.randn(shape, generator=generator, device=gdev, dtype=dtype)
+    return x.to(device) if device is not None else x
+
+
+class GraphedDenoiser:
+    """One denoising step ``x <- cx * x + ce * unet(x, t)`` captured in a CUDA graph.
+
+    ``x`` (NHWC, updated in place), ``t`` [B] and ``coef`` [2] are static device buffers."""
+
+    def __init__(self, unet: UNet2DModel, batch: int, warmup: int = 2):
+        dev = unet.device
+        c, s = unet.config.in_channels, unet.config.sample_size
+        self.unet = unet
+        self.x = torch.zeros((batch, s, s, c), dtype=torch.float32, device=dev)
+        self.t = torch.ones((batch,), dtype=torch.float32, device=dev)
+        self.coef = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
+        self.eps = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.x.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops._lib.launch_count()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self._body()
+        self.launches_per_step = ops._lib.launch_count() - n0
+
+    def _body(self):
+        eps = self.unet(ops.nchw_view(self.x), self.t, return_dict=False)[0]
+        self.eps = ops.nhwc(eps)
+        ops.axpby(self.x, self.eps, self.coef, None, out=self.x)
+
+    def replay(self):
+        self.graph.replay()
+
+
+class MyLDMPipeline:
+    def __init__(self, vae: AliasFreeAutoencoderKL, unet: UNet2DModel, scheduler: DDIMScheduler):
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self._graphs = {}
+        self._bar = {}
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_config(cls, unet_config=FFHQ_UNET, vae_config=FFHQ_AFVAE, scheduler_config=FFHQ_DDIM,
+                    seed: int = 0, alias_free: bool = True, with_vae: bool = True):
+        """Randomly initialised pipeline of the released architecture (no checkpoint is reachable
+        offline).  Weights follow PyTorch's default initialisers under ``seed``."""
+        torch.manual_seed(seed)
+        unet = UNet2DModel.from_config(unet_config)
+        if alias_free:
+            make_af_unet(unet)
+        vae = AliasFreeAutoencoderKL.from_config(vae_config) if with_vae else None
+        return cls(vae, unet, DDIMScheduler.from_config(scheduler_config))
+
+    def to(self, device):
+        self.unet.to(device)
+        if self.vae is not None:
+            self.vae.to(device)
+        self._graphs.clear()
+        return self
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    def set_progress_bar_config(self, **kwargs):
+        self._bar = kwargs
+
+    def progress_bar(self, iterable):
+        if self._bar.get("disable", True):
+            return iterable
+        from tqdm import tqdm
+        return tqdm(iterable, **{k: v for k, v in self._bar.items() if k != "disable"})
+
+    # ------------------------------------------------------------------ denoising
+    def graphed(self, batch: int) -> GraphedDenoiser:
+        g = self._graphs.get(batch)
+        if g is None:
+            g = self._graphs[batch] = GraphedDenoiser(self.unet, batch)
+        return g
+
+    def step_tables(self, num_inference_steps: int, batch: int):
+        """Device tables [steps, B] of timesteps and [steps, 2] of DDIM coefficients."""
+        self.scheduler.set_timesteps(num_inference_steps)
+        ts = self.scheduler.timesteps
+        coefs = torch.stack([torch.stack(self.scheduler.coefficients(int(t))) for t in ts]).to(torch.float32)
+        tt = ts.to(torch.float32)[:, None].expand(-1, batch).contiguous()
+        return tt.to(self.device), coefs.to(self.device)
+
+    @torch.no_grad()
+    def denoise(self, latents: torch.Tensor, num_inference_steps: int = 50, use_cuda_graph: bool = True):
+        """DDIM loop of ldm_pipeline.py:103-109 (eta = 0) on device-resident latents [B,C,H,W]."""
+        latents = latents.to(device=self.device, dtype=torch.float32)
+        if not use_cuda_graph:
+            self.scheduler.set_timesteps(num_inference_steps)
+            for t in self.progress_bar(self.scheduler.timesteps):
+                eps = self.unet(self.scheduler.scale_model_input(latents, t), int(t)).sample
+                latents = self.scheduler.step(eps, int(t), latents).prev_sample
+            return ops.to_nchw_contiguous(ops.nhwc(latents))
+        g = self.graphed(latents.shape[0])
+        tt, coefs = self.step_tables(num_inference_steps, latents.shape[0])
+        g.x.copy_(ops.nhwc(latents))
+        for i in self.progress_bar(range(num_inference_steps)):
+            g.t.copy_(tt[i])
+            g.coef.copy_(coefs[i])
+            g.replay()
+        return ops.to_nchw_contiguous(g.x)
+
+    @torch.no_grad()
+    def __call__(self, batch_size: int = 1, generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+                 eta: float = 0.0, num_inference_steps: int = 50, latents=None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, use_cuda_graph: bool = True, **kwargs):
+        if eta != 0.0:
+            raise NotImplementedError("eta > 0 is not on the AF-LDM path")
+        if latents is None:
+            latents = randn_tensor((batch_size, self.unet.config.in_channels, self.unet.config.sample_size,
+                                    self.unet.config.sample_size), generator=generator)
+        latents = latents.to(device=self.device, dtype=self.unet.dtype) * self.scheduler.init_noise_sigma
+        latents = self.denoise(latents, num_inference_steps, use_cuda_graph)
+        if output_type == "latent":
+            return latents
+        image = self.decode_latents(latents)
+        if output_type != "pt":
+            image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
+            if output_type == "pil":
+                from PIL import Image
+                image = [Image.fromarray((im * 255).round().astype("uint8")) for im in image]
+            return ImagePipelineOutput(images=image) if return_dict else (image,)
+        return image
+
+    @torch.no_grad()
+    def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """ldm_pipeline.py:117-119."""
+        return self.vae.decode(latents / self.vae.config.scaling_factor).sample
+
+    @torch.no_grad()
+    def ddim_inversion(self, latent: torch.Tensor, bar: bool = True) -> torch.Tensor:
+        """ldm_pipeline.py:133-160: deterministic DDIM run backwards over ``scheduler.timesteps``."""
+        sch = self.scheduler
+        timesteps = sch.timesteps.flip(0)
+        latent = latent.to(device=self.device, dtype=torch.float32)
+        for i, t in enumerate(timesteps):
+            a_t = sch.alphas_cumprod[int(t)]
+            a_prev = sch.alphas_cumprod[int(timesteps[i - 1])] if i > 0 else sch.final_alpha_cumprod
+            mu, mu_prev = a_t ** 0.5, a_prev ** 0.5
+            sigma, sigma_prev = (1 - a_t) ** 0.5, (1 - a_prev) ** 0.5
+            eps = self.unet(latent, int(t)).sample
+            # latent' = mu * (latent - sigma_prev * eps) / mu_prev + sigma * eps
+            cx = float(mu / mu_prev)
+            ce = float(sigma - mu * sigma_prev / mu_prev)
+            latent = ops.nchw_view(ops.axpby(ops.nhwc(latent), ops.nhwc(eps), cx, ce))
+        return ops.to_nchw_contiguous(ops.nhwc(latent))

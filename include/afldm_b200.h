@@ -98,7 +98,8 @@ AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int 
  * (diffusers ResnetBlock2D conv1/conv2/conv_shortcut, Up/Downsample2D.conv with the stride
  *  forced to 1 by af_blocks.py:129, Attention to_q/to_k/to_v/to_out as k = 1).
  * x has row pitch x_pitch floats per pixel (>= Cin); w is PACKED [Cout][k*k][Cin] (tap-major,
- * Cin contiguous); bias [Cout] | NULL, row_add [B][Cout] | NULL (time-embedding projection),
+ * Cin contiguous); bias [Cout] | NULL, row_add [B][Cout] with row pitch row_add_pitch | NULL
+ * (time-embedding projection; a slice of the batched projection of all resnets),
  * residual NHWC with row pitch res_pitch | NULL (may alias y).  y has row pitch y_pitch
  * (>= Cout) so an output can be written straight into a channel slice of a concat buffer.
  * algo: AFLDM_CONV_SIMT_F32 = fp32 FMA (exact-fp32 class; any Cin/Cout),
@@ -108,7 +109,7 @@ AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int 
  * workspace: split-K partial sums, afldm_conv2d_workspace_floats(...) floats (may be 0). */
 AFLDM_API size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
-                     const float* row_add, const float* residual, int res_pitch,
+                     const float* row_add, int row_add_pitch, const float* residual, int res_pitch,
                      float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
                      int algo, float* workspace, size_t workspace_floats, afldm_stream_t stream);
 
@@ -127,6 +128,12 @@ AFLDM_API int afldm_attention_f32(const float* q, int q_pitch, const float* k, c
                         float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
                         afldm_stream_t stream);
 
+/* In-place row softmax: x[r][:] = softmax(scale * x[r][:]) over `cols` entries, row pitch `pitch`.
+ * Used by the large-head-dim attention (VAE mid block: 1 head of 512) which runs as
+ * GEMM (q k^T) -> softmax -> GEMM (p v) through afldm_conv2d_f32 with ksize = 1. */
+AFLDM_API int afldm_softmax_rows_f32(float* x, long long rows, int cols, int pitch, float scale,
+                                     afldm_stream_t stream);
+
 /* ---- small ops of one denoising step --------------------------------------------------------
  * diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t f_k) | sin(t f_k)],
  * f_k = exp(-ln(10000) k / (dim/2)). */
@@ -142,6 +149,11 @@ AFLDM_API int afldm_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int
  * passed as the two host-computed coefficients  out = cx*x + ce*eps.  out may alias x. */
 AFLDM_API int afldm_axpby_f32(const float* x, const float* eps, float* out, float cx, float ce, long long n,
                     afldm_stream_t stream);
+
+/* Same update with the two coefficients read from DEVICE memory (coef[0] = cx, coef[1] = ce), so a
+ * captured CUDA graph of one denoising step can be replayed for every timestep. */
+AFLDM_API int afldm_axpby_dev_f32(const float* x, const float* eps, float* out, const float* coef,
+                                  long long n, afldm_stream_t stream);
 
 /* ---- StyleGAN3 upfirdn2d (afldm/af_libs/torch_utils/ops/upfirdn2d.cpp:16; BASELINE config #1)
  * x NCHW [B,C,H,W] contiguous, f [fh][fw] (2-D, already normalised; gain applied here),

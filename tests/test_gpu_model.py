@@ -1,0 +1,181 @@
+"""GPU parity of the host-side module mirror (afldm_b200.models / af_modules / pipelines) against
+the oracle's restated diffusers blocks with IDENTICAL weights (state_dicts are interchangeable).
+fp32 everywhere; the torch reference runs with TF32 disabled."""
+import pytest
+import torch
+
+from afldm_b200 import _lib, ops
+from afldm_b200.af_modules import af_api
+from afldm_b200.models import UNet2DModel
+from afldm_b200.models import blocks as B
+from afldm_b200.pipelines import AttnState, CrossFrameAttnProcessor, MyLDMPipeline, set_unet_attn_processor
+from afldm_b200.schedulers import DDIMScheduler
+from oracle import af_blocks as OA
+from oracle import cross_frame as OC
+from oracle import nn as ON
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SMALL = dict(block_out_channels=[64, 128, 128], down_block_types=["AttnDownBlock2D", "AttnDownBlock2D", "DownBlock2D"],
+             up_block_types=["UpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D"], attention_head_dim=8, sample_size=16)
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _exact_torch_reference():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ops.set_default_conv_algo("simt")
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def randn(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(DEV)
+
+
+def jitter(module, seed=0):
+    """Non-trivial norm affines / biases so that every parameter matters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.add_(torch.randn(p.shape, generator=g).to(p.device) * 0.1)
+            elif n.endswith("bias"):
+                p.add_(torch.randn(p.shape, generator=g).to(p.device) * 0.05)
+
+
+def pair(mine, ref, seed=0):
+    torch.manual_seed(seed)
+    ref = ref.to(DEV)
+    jitter(ref, seed)
+    mine = mine.to(DEV)
+    mine.load_state_dict(ref.state_dict())
+    return mine.eval(), ref.eval()
+
+
+@pytest.mark.parametrize("cin,cout,n,af", [(192, 192, 32, True), (576, 192, 32, True), (1536, 768, 2, True),
+                                            (384, 384, 16, False), (768, 384, 8, True)])
+def test_resnet_block(cin, cout, n, af):
+    mine, ref = pair(B.ResnetBlock2D(cin, cout, 768), ON.ResnetBlock2D(cin, cout, 768), seed=cin)
+    if af:
+        mine.nonlinearity = af_api.wrap_nonlinearity(mine.nonlinearity)
+        ref.nonlinearity = OA.WarpedNonlinearity(ref.nonlinearity)
+    x, temb = randn(2, cin, n, n, seed=1), randn(2, 768, seed=2)
+    with torch.no_grad():
+        want = ref(x, temb)
+        got = mine(x, temb)
+    torch.testing.assert_close(got.contiguous(), want, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("c,n,heads", [(192, 32, 8), (384, 16, 16), (768, 2, 32)])
+def test_attention_block(c, n, heads):
+    mine, ref = pair(B.Attention(c, heads, c // heads), ON.Attention(c, heads, c // heads), seed=c)
+    x = randn(2, c, n, n, seed=3)
+    with torch.no_grad():
+        torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=0, atol=1e-4)
+
+
+def test_alias_free_resamplers():
+    d_mine, d_ref = pair(B.Downsample2D(192, True, 192, padding=1), ON.Downsample2D(192, True, 192, padding=1))
+    d_mine, d_ref = af_api.replace_downsampler(d_mine), OA.AliasFreeDownsample2D(192, True, 192, 1, d_ref.conv)
+    x = randn(2, 192, 32, 32, seed=4)
+    with torch.no_grad():
+        torch.testing.assert_close(d_mine(x).contiguous(), d_ref(x), rtol=0, atol=5e-5)
+    u_mine, u_ref = pair(B.Upsample2D(384, True, 384), ON.Upsample2D(384, True, 384))
+    u_mine, u_ref = af_api.replace_upsampler(u_mine), OA.AliasFreeUpsample2D(384, True, 384, u_ref.conv)
+    x = randn(2, 384, 16, 16, seed=5)
+    with torch.no_grad():
+        torch.testing.assert_close(u_mine(x).contiguous(), u_ref(x), rtol=0, atol=5e-5)
+    # padding == 0 variant (VAE encoder, af_blocks.py:142-144)
+    p_mine, p_ref = pair(B.Downsample2D(64, True, 64, padding=0), ON.Downsample2D(64, True, 64, padding=0))
+    p_mine, p_ref = af_api.replace_downsampler(p_mine), OA.AliasFreeDownsample2D(64, True, 64, 0, p_ref.conv)
+    x = randn(1, 64, 16, 16, seed=6)
+    with torch.no_grad():
+        torch.testing.assert_close(p_mine(x).contiguous(), p_ref(x), rtol=0, atol=5e-5)
+
+
+def test_warped_nonlinearity_module_dropin():
+    m = af_api.wrap_nonlinearity(torch.nn.SiLU())
+    r = OA.WarpedNonlinearity(torch.nn.SiLU())
+    x = randn(2, 64, 8, 8, seed=7)                                   # plain NCHW-contiguous input
+    torch.testing.assert_close(m(x).contiguous(), r(x), rtol=0, atol=1e-5)
+    t = randn(4, 768, seed=8)                                        # ndim < 4: plain activation
+    torch.testing.assert_close(m(t), r(t), rtol=0, atol=2e-6)
+
+
+def _small_unets(seed=0):
+    mine, ref = pair(UNet2DModel.from_config(SMALL), ON.UNet2DModel(**SMALL), seed=seed)
+    af_api.make_af_unet(mine)
+    OA.make_af_unet(ref)
+    return mine, ref
+
+
+def test_small_unet_forward_and_ddim_trajectory():
+    mine, ref = _small_unets()
+    x = randn(3, 4, 16, 16, seed=9)
+    with torch.no_grad():
+        want = ref(x, torch.tensor(501, device=DEV)).sample
+        got = mine(x, 501).sample
+        torch.testing.assert_close(got.contiguous(), want, rtol=0, atol=2e-4)
+        got_t = mine(x, torch.tensor([501.0] * 3, device=DEV), return_dict=False)[0]
+        assert torch.equal(got_t, got)
+        # 10 DDIM steps: trajectory drift stays small
+        sm, sr = DDIMScheduler.from_config(), ON.DDIMScheduler()
+        sm.set_timesteps(10)
+        sr.set_timesteps(10)
+        a, b = x, x
+        for t in sm.timesteps:
+            a = sm.step(mine(a, int(t)).sample, int(t), a).prev_sample
+            b = sr.step(ref(b, t.to(DEV)).sample, int(t), b, return_dict=False)[0]
+        torch.testing.assert_close(a.contiguous(), b, rtol=0, atol=1e-3)
+
+
+def test_graphed_denoise_equals_eager():
+    mine, _ = _small_unets(seed=1)
+    pipe = MyLDMPipeline(None, mine, DDIMScheduler.from_config())
+    x = randn(2, 4, 16, 16, seed=10)
+    eager = pipe.denoise(x, 6, use_cuda_graph=False)
+    n0 = _lib.launch_count()
+    graphed = pipe.denoise(x, 6, use_cuda_graph=True)
+    assert torch.equal(eager, graphed)                              # same kernels, same order: bitwise
+    assert pipe.graphed(2).launches_per_step > 50
+    again = pipe.denoise(x, 6, use_cuda_graph=True)                 # replay of the cached graph
+    assert torch.equal(again, graphed)
+    assert _lib.launch_count() >= n0
+
+
+def test_cross_frame_attention_store_load():
+    mine, ref = _small_unets(seed=2)
+    st_m, st_r = AttnState(), OC.AttnState()
+    set_unet_attn_processor(mine, {k: CrossFrameAttnProcessor(st_m) for k in
+                                   __import__("afldm_b200.pipelines.cross_frame_attn", fromlist=["x"]).get_unet_attn_processors(mine)})
+    OC.set_attn_processor(ref, lambda: OC.CrossFrameAttnProcessor(st_r))
+    x0, x1 = randn(1, 4, 16, 16, seed=11), randn(4, 4, 16, 16, seed=12)
+    with torch.no_grad():
+        for st in (st_m, st_r):
+            st.reset()
+            st.set_timestep(torch.tensor(301))
+        a0, b0 = mine(x0, 301).sample, ref(x0, torch.tensor(301, device=DEV)).sample
+        torch.testing.assert_close(a0.contiguous(), b0, rtol=0, atol=2e-4)
+        st_m.to_load()
+        st_r.to_load()
+        a1, b1 = mine(x1, 301).sample, ref(x1, torch.tensor(301, device=DEV)).sample    # K/V of frame 0, batch 4
+        torch.testing.assert_close(a1.contiguous(), b1, rtol=0, atol=2e-4)
+        assert (a1 - mine(x1, 301).sample).abs().max() == 0
+
+
+@pytest.mark.slow
+def test_full_ffhq_unet_step_vs_oracle():
+    """BASELINE config #2 architecture (256.4 M parameters), B = 2, one forward."""
+    mine, ref = pair(UNet2DModel.from_config(), ON.UNet2DModel(), seed=0)
+    af_api.make_af_unet(mine)
+    OA.make_af_unet(ref)
+    x = randn(2, 4, 32, 32, seed=0)
+    with torch.no_grad():
+        want = ref(x, torch.tensor(981, device=DEV)).sample
+        got = mine(x, 981).sample
+    err = (got - want).abs().max().item()
+    assert err < 5e-4 * max(1.0, want.abs().max().item()), err
