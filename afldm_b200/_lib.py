@@ -42,7 +42,7 @@ SIGNATURES = {
     "afldm_nhwc_to_nchw_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "afldm_axpby_f32": (_i, [_p, _p, _p, _f, _f, _ll, _p]),
     "afldm_axpby_dev_f32": (_i, [_p, _p, _p, _p, _ll, _p]),
-    "afldm_upfirdn2d_f32": (_i, [_p, _p, _p] + [_i] * 16 + [_f, _p]),
+    "afldm_upfirdn2d_f32": (_i, [_p, _p, _p] + [_i] * 15 + [_f, _p]),
 }
 
 _lib = None

@@ -157,11 +157,13 @@ def test_conv2d_simt_vs_torch(b, h, w, cin, cout, k):
     bias = randn(cout, seed=3)
     row = randn(b, cout, seed=4)
     res = randn(b, cout, h, w, seed=5)
-    want = F.conv2d(x, wt, bias, padding=k // 2) + row[:, :, None, None] + res
+    # fp64 reference: both cuDNN-fp32 and this kernel round differently over K = k*k*Cin terms
+    conv64 = F.conv2d(x.double(), wt.double(), None, padding=k // 2)
+    want = (conv64 + bias.double()[None, :, None, None] + row.double()[:, :, None, None] + res.double()).float()
     got = ops.conv2d(to_nhwc(x), ops.pack_conv_weight(wt), bias, k, row_add=row, residual=to_nhwc(res), algo="simt")
     torch.testing.assert_close(to_nchw(got), want, rtol=0, atol=2e-5)
     plain = ops.conv2d(to_nhwc(x), ops.pack_conv_weight(wt), None, k, algo="simt")
-    torch.testing.assert_close(to_nchw(plain), F.conv2d(x, wt, None, padding=k // 2), rtol=0, atol=2e-5)
+    torch.testing.assert_close(to_nchw(plain), conv64.float(), rtol=0, atol=2e-5)
 
 
 def test_conv2d_pitched_views_and_inplace_residual():
