@@ -1,15 +1,433 @@
-// tcgen05 (TF32, TMEM accumulators, TMA operand staging) implicit-GEMM convolution.
-// Placeholder until the tensor-core path lands: every shape reports "no kernel".
+// tcgen05 implicit-GEMM convolution (k = 1 / 3, stride 1, "same" padding) for sm_100a:
+// TF32 operands from shared memory, fp32 accumulators in TMEM, operands staged by TMA.
+//
+// GEMM view: D[M = B*H*W pixels][N = Cout] = A[M][K] * W[N][K]^T, K = taps * Cin, k = tap*Cin + ci.
+//
+//  * A (im2col) is never materialised.  The NHWC activation is one 4-D TMA tensor {C, W, H, B};
+//    the 128 output pixels of a CTA tile are a box {32 ch, BW, BH, BB} of it, and filter tap
+//    (kh, kw) is the SAME box shifted by (kw-1, kh-1) - TMA zero-fills whatever falls outside
+//    the image, which is exactly the conv's zero padding.  Each box lands in shared memory as
+//    128 rows x 128 B (K-major, 128B-swizzled), the canonical tcgen05 operand layout.
+//  * W is a 2-D TMA tensor {K, Cout} (weights packed [Cout][tap][Cin]); box {32, BN}.
+//  * One CTA = one 128 x BN output tile (BN in 32..256): warp 0 issues TMA into an
+//    N-stage mbarrier ring, warp 1 issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; four per
+//    stage) and commits each stage back to the producer, warps 2-5 read the accumulator with
+//    tcgen05.ld (one TMEM lane = one output pixel per thread) and apply the fused epilogue
+//    (+bias +time-embedding row +residual) straight to global memory.
+//  * Small-M layers (8x8 ... 2x2 levels, weight-stream bound) are split along K over
+//    blockIdx.z; partial tiles go to the caller workspace and are reduced deterministically.
+//
+// Numeric class: TF32 (10-bit mantissa) products, fp32 accumulation - the same class as the
+// reference's default cuDNN path (torch.backends.cudnn.allow_tf32 = True).
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
 #include "common.cuh"
 #include "conv.cuh"
 
 namespace afldm {
+namespace {
 
-bool conv_tc_workspace_floats(int, int, int, int, int, int, size_t*) { return false; }
+constexpr int TBM = 128;           // output pixels per tile (UMMA M)
+constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
+constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
+constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 
-int conv_tc_launch(const float*, int, const float*, const float*, const float*, int, const float*, int, float*,
-                   int, int, int, int, int, int, int, float*, size_t, cudaStream_t) {
-    return AFLDM_E_NOKERNEL;
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30),
+// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version = 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+struct TcArgs {
+    const float* bias;
+    const float* row_add;
+    const float* residual;
+    float* y;
+    float* ws;
+    int row_add_pitch, res_pitch, y_pitch;
+    int M, Cout, HW;
+    int taps, ks, cin_chunks;       // K iteration space: taps x cin_chunks stages of 32
+    int iters_per_split;
+    int BN, stages, tmem_cols;
+    int W, H;                       // image size
+    int BW, BH;                     // box geometry (BB implied)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t accum_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int b_stage_bytes = a.BN * TBK * 4;
+    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+
+    const int total_iters = a.taps * a.cin_chunks;
+    const int it_beg = blockIdx.z * a.iters_per_split;
+    const int it_end = min(total_iters, it_beg + a.iters_per_split);
+    const int n_iters = it_end - it_beg;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&accum_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_slot)), "r"((uint32_t)a.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int m0 = blockIdx.x * TBM;
+    const int n0 = blockIdx.y * a.BN;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0 && n_iters > 0) {
+            // tile origin in (w, h, b)
+            int w0, h0, b0;
+            if (a.W >= TBM) {
+                const int per_row = a.W / TBM;
+                const int row = blockIdx.x / per_row;
+                w0 = (blockIdx.x % per_row) * TBM;
+                h0 = row % a.H;
+                b0 = row / a.H;
+            } else if (a.BH == a.H) {
+                w0 = 0; h0 = 0;
+                b0 = blockIdx.x * (TBM / (a.W * a.H));
+            } else {
+                const int per_img = a.H / a.BH;
+                w0 = 0;
+                h0 = (blockIdx.x % per_img) * a.BH;
+                b0 = blockIdx.x / per_img;
+            }
+            const int pad = a.ks >> 1;
+            for (int i = 0; i < n_iters; ++i) {
+                const int s = i % a.stages;
+                const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const int it = it_beg + i;
+                const int tap = it / a.cin_chunks;
+                const int c0 = (it - tap * a.cin_chunks) * TBK;
+                const int dh = tap / a.ks - pad, dw = tap % a.ks - pad;
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                const uint32_t sa = smem_base + s * stage_bytes;
+                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0 && n_iters > 0) {
+            // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both,
+            // N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
+                                   ((uint32_t)(TBM >> 4) << 24);
+            for (int i = 0; i < n_iters; ++i) {
+                const int s = i % a.stages;
+                const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_base + s * stage_bytes;
+                const uint64_t da = make_desc(sa), db = make_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TBK / UMMA_K; ++k) {
+                    // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                    umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&empty_bar[s]));   // frees the stage when these MMAs retire
+            }
+            umma_commit(smem_u32(&accum_bar));          // accumulator complete
+        }
+    } else {
+        // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                  // TMEM lane == local output pixel
+        const int m = m0 + row;
+        const bool split = gridDim.z > 1;
+        if (n_iters > 0) {
+            mbar_wait(smem_u32(&accum_bar), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int bimg = (m < a.M) ? m / a.HW : 0;
+        for (int c = 0; c < a.BN; c += 16) {
+            uint32_t r[16];
+            if (n_iters > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            if (m >= a.M) continue;
+            const int n = n0 + c;
+            if (split) {
+                float* dst = a.ws + ((size_t)blockIdx.z * a.M + m) * a.Cout + n;
+                if (n + 16 <= a.Cout && (a.Cout & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < a.Cout) dst[j] = __uint_as_float(r[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (n + j >= a.Cout) continue;
+                    float v = __uint_as_float(r[j]);
+                    if (a.bias != nullptr) v += a.bias[n + j];
+                    if (a.row_add != nullptr) v += a.row_add[(size_t)bimg * a.row_add_pitch + n + j];
+                    if (a.residual != nullptr) v += a.residual[(size_t)m * a.res_pitch + n + j];
+                    r[j] = __float_as_uint(v);
+                }
+                float* dst = a.y + (size_t)m * a.y_pitch + n;
+                if (n + 16 <= a.Cout && (a.y_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < a.Cout) dst[j] = __uint_as_float(r[j]);
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct TcPlan {
+    bool ok;
+    int M, mtiles, ntiles, BN, stages, tmem_cols, total_iters, splitk, iters_per_split, BW, BH, BB;
+    size_t smem_bytes;
+};
+
+TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
+    TcPlan p{};
+    p.ok = false;
+    if (Cin % TBK != 0 || Cout % 16 != 0 || !is_pow2(W) || !is_pow2(H)) return p;
+    if (W > TBM && W % TBM != 0) return p;
+    p.M = B * H * W;
+    p.mtiles = ceil_div(p.M, TBM);
+    if (W >= TBM) { p.BW = TBM; p.BH = 1; p.BB = 1; }
+    else {
+        p.BW = W;
+        p.BH = std::min(H, TBM / W);
+        p.BB = TBM / (W * p.BH);
+    }
+    if (p.BB > 1 && p.BH != H) return p;
+    if (p.BB > 256) return p;
+    p.total_iters = ks * ks * (Cin / TBK);
+
+    // Tile width: largest BN (multiple of 32, divides into <= 256) whose grid still fills the chip; small
+    // problems take BN = 64 and split K instead.
+    const int cands[] = {256, 192, 128, 96, 64, 32};
+    int best = 0;
+    for (int bn : cands) {
+        if (bn > Cout && bn != 32) continue;
+        if (Cout % bn != 0 && bn > 64) continue;
+        const int tiles = p.mtiles * ceil_div(Cout, bn);
+        if (tiles >= 120) { best = bn; break; }
+    }
+    if (best == 0) best = Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16);
+    if (best > Cout) best = Cout;        // Cout in {16, 32, 48}: one narrow tile
+    p.BN = best;
+    p.ntiles = ceil_div(Cout, p.BN);
+    const int tiles = p.mtiles * p.ntiles;
+    int s = 1;
+    if (tiles < 100) {
+        s = ceil_div(2 * 148, tiles);
+        s = std::min(s, std::max(1, p.total_iters / 4));   // >= 4 stages of 32 k per split
+        s = std::min(s, 64);
+    }
+    p.iters_per_split = ceil_div(p.total_iters, s);
+    p.splitk = ceil_div(p.total_iters, p.iters_per_split);
+    const int stage_bytes = A_STAGE_BYTES + p.BN * TBK * 4;
+    p.stages = std::max(2, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
+    p.stages = std::min(p.stages, std::max(2, p.iters_per_split));
+    p.smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+    p.ok = true;
+    return p;
+}
+
+}  // namespace
+
+bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    if (!p.ok) return false;
+    *floats = p.splitk > 1 ? (size_t)p.splitk * p.M * Cout : 0;
+    return true;
+}
+
+int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
+                   int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H,
+                   int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, cudaStream_t st) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    if (!p.ok || (x_pitch & 3) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) return AFLDM_E_NOKERNEL;
+    if (p.splitk > 1 && (workspace == nullptr || workspace_floats < (size_t)p.splitk * p.M * Cout))
+        return AFLDM_E_WORKSPACE;
+
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * W,
+                                       (cuuint64_t)x_pitch * 4 * W * H};
+        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BB};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return AFLDM_E_NOKERNEL;
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)ks * ks * Cin;
+        const cuuint64_t dims[2] = {K, (cuuint64_t)Cout};
+        const cuuint64_t strides[1] = {K * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)p.BN};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return AFLDM_E_NOKERNEL;
+    }
+
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BUDGET + 8 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    TcArgs a;
+    a.bias = bias; a.row_add = row_add; a.residual = residual; a.y = y; a.ws = workspace;
+    a.row_add_pitch = row_add_pitch; a.res_pitch = res_pitch; a.y_pitch = y_pitch;
+    a.M = p.M; a.Cout = Cout; a.HW = H * W;
+    a.taps = ks * ks; a.ks = ks; a.cin_chunks = Cin / TBK;
+    a.iters_per_split = p.iters_per_split;
+    a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+    a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
+    dim3 grid(p.mtiles, p.ntiles, p.splitk);
+    conv_tc_kernel<<<grid, TC_THREADS, p.smem_bytes, st>>>(map_a, map_b, a);
+    int launches = 1;
+    if (p.splitk > 1) {
+        splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch,
+                             p.M, Cout, H * W, st);
+        ++launches;
+    }
+    return launched(launches);
 }
 
 }  // namespace afldm

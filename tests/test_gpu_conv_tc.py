@@ -1,0 +1,95 @@
+"""GPU parity of the tcgen05 / TMA convolution (AFLDM_CONV_TCGEN05_TF32) against an fp64 reference.
+
+Numeric class: operands rounded to TF32 (10-bit mantissa), fp32 accumulation in TMEM - the class of
+the reference's own default GPU path (cuDNN with allow_tf32).  For O(1) outputs of K = k*k*Cin
+random products the expected error is ~7e-4 rms; the stated tolerance is 8e-3 max / 1.5e-3 mean.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from afldm_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def randn(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(DEV)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def run_tc(*args, **kw):
+    rec = []
+    ops.record_to(rec)
+    try:
+        out = ops.conv2d(*args, algo="tf32", **kw)
+    finally:
+        ops.record_to(None)
+    return out, [r[0] for r in rec]
+
+
+TC_CASES = [  # B, H, W, Cin, Cout, k      (every conv family of the FFHQ UNet + VAE-like planes)
+    (2, 32, 32, 192, 192, 3), (16, 32, 32, 192, 192, 3), (2, 32, 32, 576, 192, 3), (2, 32, 32, 192, 576, 1),
+    (4, 16, 16, 384, 384, 3), (2, 16, 16, 768, 384, 1), (2, 16, 16, 384, 1152, 1),
+    (16, 8, 8, 384, 384, 3), (3, 4, 4, 768, 768, 3), (16, 2, 2, 1536, 768, 3), (16, 2, 2, 768, 2304, 1),
+    (1, 64, 64, 128, 128, 3), (1, 128, 128, 64, 32, 3), (1, 256, 256, 32, 16, 3), (5, 1, 1, 64, 64, 1),
+    (2, 1024, 1, 192, 384, 1),
+]
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,k", TC_CASES)
+def test_conv2d_tcgen05_vs_fp64(b, h, w, cin, cout, k):
+    x = randn(b, cin, h, w, seed=cin + h)
+    wt = randn(cout, cin, k, k, seed=cout) * (1.0 / (cin * k * k) ** 0.5)
+    bias, row, res = randn(cout, seed=3), randn(b, cout, seed=4), randn(b, cout, h, w, seed=5)
+    conv64 = F.conv2d(x.double(), wt.double(), None, padding=k // 2)
+    want = (conv64 + bias.double()[None, :, None, None] + row.double()[:, :, None, None] + res.double()).float()
+    got, names = run_tc(nhwc(x), ops.pack_conv_weight(wt), bias, k, row_add=row, residual=nhwc(res))
+    assert names == ["conv2d_tf32"], f"tensor-core path did not run for this shape: {names}"
+    err = (got.permute(0, 3, 1, 2) - want).abs()
+    assert err.max().item() < 8e-3 and err.mean().item() < 1.5e-3, (err.max().item(), err.mean().item())
+    # TF32-exact inputs (values representable in 10 mantissa bits) must reproduce fp32 FMA results closely
+    xq = (x * 8).round() / 8
+    wq = (wt * 64).round() / 64
+    got_q, _ = run_tc(nhwc(xq), ops.pack_conv_weight(wq), None, k)
+    want_q = F.conv2d(xq.double(), wq.double(), None, padding=k // 2).float()
+    torch.testing.assert_close(got_q.permute(0, 3, 1, 2), want_q, rtol=0, atol=2e-4)
+
+
+def test_tcgen05_pitched_views_and_inplace_residual():
+    b, h, w, cin, cout = 2, 16, 16, 64, 96
+    big_in = nhwc(randn(b, cin + 32, h, w, seed=1))
+    big_out = torch.zeros(b, h, w, cout + 64, device=DEV)
+    wt = ((randn(cout, cin, 3, 3, seed=2) * 0.05) * 256).round() / 256
+    res0 = randn(b, h, w, cout, seed=3)
+    big_out[..., 64:] = res0
+    xq = (big_in[..., 32:] * 8).round() / 8
+    big_in[..., 32:] = xq
+    out = big_out[..., 64:]
+    _, names = run_tc(big_in[..., 32:], ops.pack_conv_weight(wt), None, 3, residual=out, out=out)
+    assert names == ["conv2d_tf32"]
+    want = F.conv2d(xq.permute(0, 3, 1, 2).double(), wt.double(), None, padding=1).float() + res0.permute(0, 3, 1, 2)
+    torch.testing.assert_close(big_out[..., 64:].permute(0, 3, 1, 2), want, rtol=0, atol=2e-4)
+    assert big_out[..., :64].abs().max() == 0
+
+
+def test_tcgen05_falls_back_to_simt_outside_its_family():
+    x = nhwc(randn(2, 4, 32, 32, seed=1))                        # conv_in: Cin = 4
+    wt = randn(192, 4, 3, 3, seed=2) * 0.1
+    got, names = run_tc(x, ops.pack_conv_weight(wt), None, 3)
+    assert names == ["conv2d_simt"]
+    torch.testing.assert_close(got.permute(0, 3, 1, 2), F.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), padding=1).float(),
+                               rtol=0, atol=2e-5)
+
+
+def test_tcgen05_split_k_is_deterministic():
+    x = nhwc(randn(16, 1536, 2, 2, seed=1))
+    wp = ops.pack_conv_weight(randn(768, 1536, 3, 3, seed=2) * 0.01)
+    a, _ = run_tc(x, wp, None, 3)
+    b, _ = run_tc(x, wp, None, 3)
+    assert torch.equal(a, b)
