@@ -34,7 +34,7 @@ SIGNATURES = {
     "afldm_conv2d_workspace_floats": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "afldm_conv2d_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "afldm_linear_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "afldm_attention_f32": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "afldm_attention_f32": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_softmax_rows_f32": (_i, [_p, _ll, _i, _i, _f, _p]),
     "afldm_timestep_embedding_f32": (_i, [_p, _p, _i, _i, _p]),
     "afldm_concat_channels_f32": (_i, [_p, _i, _p, _i, _p, _ll, _p]),

@@ -139,6 +139,158 @@ softmax_rows_kernel(float* __restrict__ x, long long rows, int cols, int pitch, 
     for (int c = lane; c < cols; c += 32) xr[c] *= inv;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant (AFLDM_ATTN_MMA_TF32): flash attention on warp-level mma.m16n8k8 TF32 with
+// fp32 accumulation and fp32 online softmax.  One warp owns 16 query rows; a CTA of 4 warps shares
+// 64-key K / V tiles in shared memory (row pitch D + 4 words: every fragment load is conflict-free).
+// The S accumulator fragment (cols 2t, 2t+1 per lane) is reused directly as the A fragment of P.V by
+// reading V rows in the matching permuted order (k = t <- key 2t, k = t + 4 <- key 2t + 1), so no
+// shuffles or shared-memory round trip are needed between the two products.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
+                     const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
+                     int Bkv_rep, int Nq, int Nk, float qscale) {
+    constexpr int KT = 64;            // keys per tile
+    constexpr int P = D + 4;          // smem row pitch (words)
+    constexpr int DK = D / 8;         // k-steps of Q.K^T == n-tiles of P.V
+    __shared__ __align__(16) float Ks[KT * P];
+    __shared__ __align__(16) float Vs[KT * P];
+    const int b = blockIdx.z, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int bkv = b / Bkv_rep;
+    const int row0 = blockIdx.x * 64 + warp * 16 + g;      // this lane's rows: row0 and row0 + 8
+    const int row1 = row0 + 8;
+
+    // Q fragments (scaled into the exp2 domain, rounded to TF32 once)
+    uint32_t qa[DK][4];
+    {
+        const float* q0 = q + ((size_t)b * Nq + min(row0, Nq - 1)) * q_pitch + head * D;
+        const float* q1 = q + ((size_t)b * Nq + min(row1, Nq - 1)) * q_pitch + head * D;
+#pragma unroll
+        for (int ks = 0; ks < DK; ++ks) {
+            qa[ks][0] = to_tf32(q0[8 * ks + t] * qscale);
+            qa[ks][1] = to_tf32(q1[8 * ks + t] * qscale);
+            qa[ks][2] = to_tf32(q0[8 * ks + t + 4] * qscale);
+            qa[ks][3] = to_tf32(q1[8 * ks + t + 4] * qscale);
+        }
+    }
+    float oacc[DK][4];
+#pragma unroll
+    for (int i = 0; i < DK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    const float* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    const float* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    constexpr int D4 = D / 4;
+
+    for (int k0 = 0; k0 < Nk; k0 += KT) {
+        const int nk = min(KT, Nk - k0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < KT * D4; idx += blockDim.x) {
+            const int key = idx / D4, c4 = idx - key * D4;
+            float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+            if (key < nk) {
+                kv4 = *reinterpret_cast<const float4*>(kbase + (size_t)(k0 + key) * kv_pitch + 4 * c4);
+                vv4 = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * kv_pitch + 4 * c4);
+            }
+            *reinterpret_cast<float4*>(&Ks[key * P + 4 * c4]) = kv4;
+            *reinterpret_cast<float4*>(&Vs[key * P + 4 * c4]) = vv4;
+        }
+        __syncthreads();
+
+        // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const float* kr = &Ks[(nt * 8 + g) * P + t];
+#pragma unroll
+            for (int ks = 0; ks < DK; ++ks)
+                mma_tf32(s[nt], qa[ks], __float_as_uint(kr[8 * ks]), __float_as_uint(kr[8 * ks + 4]));
+        }
+        // mask the tail keys, row maxima over the tile
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int key = nt * 8 + 2 * t;
+            if (key >= nk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+            if (key + 1 >= nk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);      // finite: key k0 is always valid
+        const float c0 = exp2f(m0 - n0), c1 = exp2f(m1 - n1);
+        m0 = n0; m1 = n1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int dn = 0; dn < DK; ++dn) {
+            oacc[dn][0] *= c0; oacc[dn][1] *= c0;
+            oacc[dn][2] *= c1; oacc[dn][3] *= c1;
+        }
+        // P = exp2(S - m); O += P V
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p00 = exp2f(s[nt][0] - n0), p01 = exp2f(s[nt][1] - n0);
+            const float p10 = exp2f(s[nt][2] - n1), p11 = exp2f(s[nt][3] - n1);
+            l0 += p00 + p01;
+            l1 += p10 + p11;
+            // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
+            const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
+            const float* vr0 = &Vs[(nt * 8 + 2 * t) * P + g];
+            const float* vr1 = vr0 + P;
+#pragma unroll
+            for (int dn = 0; dn < DK; ++dn)
+                mma_tf32(oacc[dn], pa, __float_as_uint(vr0[8 * dn]), __float_as_uint(vr1[8 * dn]));
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    if (row0 < Nq) {
+        float* op = o + ((size_t)b * Nq + row0) * o_pitch + head * D + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < DK; ++dn)
+            *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[dn][0] * i0, oacc[dn][1] * i0);
+    }
+    if (row1 < Nq) {
+        float* op = o + ((size_t)b * Nq + row1) * o_pitch + head * D + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < DK; ++dn)
+            *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[dn][2] * i1, oacc[dn][3] * i1);
+    }
+}
+
+template <int D>
+int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
+               int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+    const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
+    attention_mma_kernel<D><<<dim3(ceil_div(Nq, 64), heads, B), 128, 0, st>>>(
+        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
+    return launched();
+}
+
 template <int D>
 int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
            int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
@@ -166,7 +318,7 @@ extern "C" int afldm_softmax_rows_f32(float* x, long long rows, int cols, int pi
 
 extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
                                    float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
-                                   afldm_stream_t stream) {
+                                   int algo, afldm_stream_t stream) {
     if (q == nullptr || k == nullptr || v == nullptr || o == nullptr) return AFLDM_E_ARG;
     if (B <= 0 || Bkv <= 0 || Nq <= 0 || Nk <= 0 || heads <= 0 || d <= 0) return AFLDM_E_ARG;
     if (B % Bkv != 0) return AFLDM_E_SHAPE;
@@ -174,6 +326,22 @@ extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, 
     if (q_pitch < heads * d || kv_pitch < heads * d || o_pitch < heads * d) return AFLDM_E_ARG;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o)) return AFLDM_E_ARG;
     cudaStream_t st = as_stream(stream);
+    if (algo == AFLDM_ATTN_MMA_TF32) {
+#define AFLDM_ATT_MMA(D) \
+    case D: return launch_mma<D>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+        switch (d) {
+            AFLDM_ATT_MMA(8)
+            AFLDM_ATT_MMA(16)
+            AFLDM_ATT_MMA(24)
+            AFLDM_ATT_MMA(32)
+            AFLDM_ATT_MMA(40)
+            AFLDM_ATT_MMA(48)
+            AFLDM_ATT_MMA(64)
+            default: return AFLDM_E_NOKERNEL;
+        }
+#undef AFLDM_ATT_MMA
+    }
+    if (algo != AFLDM_ATTN_SIMT_F32) return AFLDM_E_ARG;
 #define AFLDM_ATT_CASE(D) \
     case D: return launch<D>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
     switch (d) {

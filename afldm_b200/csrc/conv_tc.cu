@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -34,8 +35,10 @@ constexpr int TBM = 128;           // output pixels per tile (UMMA M)
 constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
 constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 184 * 1024;          // one CTA per SM (dynamic part; ~19 KB static on top)
+constexpr int SMEM_TWO_PER_SM = 90 * 1024;       // dynamic part that still lets two CTAs share an SM
 constexpr int MAX_STAGES = 8;
+constexpr int EPI_PITCH = 36;
 constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -93,6 +96,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start address >> 4 in [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30),
 // SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version = 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
@@ -114,6 +130,7 @@ struct TcArgs {
     int BN, stages, tmem_cols;
     int W, H;                       // image size
     int BW, BH;                     // box geometry (BB implied)
+    int vec_ok;                     // all epilogue pointers / pitches allow float4 access
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -124,6 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t accum_bar;
     __shared__ uint32_t tmem_base_slot;
+    // epilogue transpose staging: per epilogue warp 32 rows x (32 + 4) floats (pitch 36: conflict-free both ways)
+    __shared__ __align__(16) float epi_stage[4][32 * EPI_PITCH];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
@@ -221,59 +240,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
         const int q = warp & 3;
-        const int row = q * 32 + lane;                  // TMEM lane == local output pixel
-        const int m = m0 + row;
         const bool split = gridDim.z > 1;
         if (n_iters > 0) {
             mbar_wait(smem_u32(&accum_bar), 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const int bimg = (m < a.M) ? m / a.HW : 0;
-        for (int c = 0; c < a.BN; c += 16) {
-            uint32_t r[16];
+        float* stg = epi_stage[q];
+        const int cq = lane & 7, rsub = lane >> 3;      // coalesced phase: 8 lanes x float4 per row, 4 rows per pass
+        for (int c = 0; c < a.BN; c += 32) {
+            uint32_t r[32];
             if (n_iters > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0u;
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m >= a.M) continue;
-            const int n = n0 + c;
-            if (split) {
-                float* dst = a.ws + ((size_t)blockIdx.z * a.M + m) * a.Cout + n;
-                if (n + 16 <= a.Cout && (a.Cout & 3) == 0) {
+            // each thread owns one accumulator row: park it in the staging tile ...
+            float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            for (int j = 0; j < 8; ++j)
+                srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            // ... and write it out 4 rows x 128 contiguous bytes per instruction
+            const int n = n0 + c + cq * 4;
+#pragma unroll
+            for (int pass = 0; pass < 8; ++pass) {
+                const int rr = pass * 4 + rsub;
+                const int mm = m0 + q * 32 + rr;
+                if (mm >= a.M || n >= a.Cout || c + cq * 4 >= a.BN) continue;
+                float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + cq * 4);
+                if (split) {
+                    *reinterpret_cast<float4*>(a.ws + ((size_t)blockIdx.z * a.M + mm) * a.Cout + n) = v;
+                } else if (a.vec_ok) {
+                    if (a.bias != nullptr) {
+                        const float4 t = *reinterpret_cast<const float4*>(a.bias + n);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    if (a.row_add != nullptr) {
+                        const float4 t = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    if (a.residual != nullptr) {
+                        const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                    }
+                    *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
                 } else {
+                    float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < a.Cout) dst[j] = __uint_as_float(r[j]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (n + j >= a.Cout) continue;
-                    float v = __uint_as_float(r[j]);
-                    if (a.bias != nullptr) v += a.bias[n + j];
-                    if (a.row_add != nullptr) v += a.row_add[(size_t)bimg * a.row_add_pitch + n + j];
-                    if (a.residual != nullptr) v += a.residual[(size_t)m * a.res_pitch + n + j];
-                    r[j] = __float_as_uint(v);
-                }
-                float* dst = a.y + (size_t)m * a.y_pitch + n;
-                if (n + 16 <= a.Cout && (a.y_pitch & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.y) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n + j < a.Cout) dst[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        float t = e[j];
+                        if (a.bias != nullptr) t += a.bias[n + j];
+                        if (a.row_add != nullptr) t += a.row_add[(size_t)(mm / a.HW) * a.row_add_pitch + n + j];
+                        if (a.residual != nullptr) t += a.residual[(size_t)mm * a.res_pitch + n + j];
+                        a.y[(size_t)mm * a.y_pitch + n + j] = t;
+                    }
                 }
             }
+            __syncwarp();
         }
     }
 
@@ -328,8 +354,11 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     if (p.BB > 256) return p;
     p.total_iters = ks * ks * (Cin / TBK);
 
-    // Tile width: largest BN (multiple of 32, divides into <= 256) whose grid still fills the chip; small
-    // problems take BN = 64 and split K instead.
+    // Tile width: largest BN (multiple of 32, <= 256) whose grid still fills the chip; small problems take
+    // BN = 64 and split K instead.  AFLDM_TC_BN / AFLDM_TC_SPLITK override the heuristic (tuning runs).
+    static const int force_bn = getenv("AFLDM_TC_BN") ? atoi(getenv("AFLDM_TC_BN")) : 0;
+    static const int force_split = getenv("AFLDM_TC_SPLITK") ? atoi(getenv("AFLDM_TC_SPLITK")) : 0;
+    static const int force_stages = getenv("AFLDM_TC_STAGES") ? atoi(getenv("AFLDM_TC_STAGES")) : 0;
     const int cands[] = {256, 192, 128, 96, 64, 32};
     int best = 0;
     for (int bn : cands) {
@@ -339,6 +368,7 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
         if (tiles >= 120) { best = bn; break; }
     }
     if (best == 0) best = Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16);
+    if (force_bn > 0 && force_bn % 16 == 0 && force_bn <= 256 && (Cout % force_bn == 0 || force_bn <= 64)) best = force_bn;
     if (best > Cout) best = Cout;        // Cout in {16, 32, 48}: one narrow tile
     p.BN = best;
     p.ntiles = ceil_div(Cout, p.BN);
@@ -349,10 +379,16 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
         s = std::min(s, std::max(1, p.total_iters / 4));   // >= 4 stages of 32 k per split
         s = std::min(s, 64);
     }
+    if (force_split > 0) s = std::min(force_split, p.total_iters);
     p.iters_per_split = ceil_div(p.total_iters, s);
     p.splitk = ceil_div(p.total_iters, p.iters_per_split);
     const int stage_bytes = A_STAGE_BYTES + p.BN * TBK * 4;
-    p.stages = std::max(2, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
+    // More CTAs than SMs and a small stage: size the ring so that two CTAs share an SM and one CTA's
+    // prologue / epilogue hides behind the other's main loop.
+    const bool two_per_sm = tiles * p.splitk > 148 && 3 * stage_bytes <= SMEM_TWO_PER_SM;
+    const int budget = two_per_sm ? SMEM_TWO_PER_SM : SMEM_BUDGET;
+    p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
+    if (force_stages > 0) p.stages = std::min(force_stages, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
     p.stages = std::min(p.stages, std::max(2, p.iters_per_split));
     p.smem_bytes = (size_t)p.stages * stage_bytes + 1024;
     p.tmem_cols = 32;
@@ -419,6 +455,9 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.iters_per_split = p.iters_per_split;
     a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
+    a.vec_ok = ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
+               (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
+               (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
     dim3 grid(p.mtiles, p.ntiles, p.splitk);
     conv_tc_kernel<<<grid, TC_THREADS, p.smem_bytes, st>>>(map_a, map_b, a);
     int launches = 1;

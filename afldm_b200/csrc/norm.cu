@@ -5,64 +5,70 @@
 // computes only the statistics (one read of x, 4 B/element) and hands the consumer kernel
 // (filtered_act / affine_act) the folded affine  y = x*scale[b,c] + shift[b,c].
 //
-//   gn_partial : grid (chunks, B), one thread per channel, fp32 sum / sum-of-squares over a
-//                chunk of <= 32 pixels (coalesced: consecutive threads = consecutive channels)
-//   gn_finalize: one warp per (b, group): fp64 reduction of the partials, mean / rstd,
-//                then scale/shift for the group's channels.
+//   gn_stats_kernel: one CTA per (b, group).  Threads stride over the group's HW x cpg elements
+//                (consecutive threads = consecutive channels of a pixel, then the next pixel), fp32
+//                partial sums per thread, fp64 block reduction, then the group's channels get their
+//                scale / shift.  One launch, no scratch, fixed reduction order (deterministic).
 #include "common.cuh"
 
 namespace afldm {
 namespace {
 
-constexpr int GN_PIX = 32;  // pixels per partial chunk
-
 __global__ void __launch_bounds__(256)
-gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int HW, int C, int nchunk) {
-    const int chunk = blockIdx.x, b = blockIdx.y;
-    const int p0 = chunk * GN_PIX;
-    const int p1 = min(HW, p0 + GN_PIX);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float* xp = x + ((size_t)b * HW + p0) * C + c;
-        float s = 0.f, q = 0.f;
-#pragma unroll 8
-        for (int p = p0; p < p1; ++p) {
-            const float v = *xp;
-            xp += C;
-            s += v;
-            q = fmaf(v, v, q);
-        }
-        float2* out = reinterpret_cast<float2*>(partial) + ((size_t)b * nchunk + chunk) * C + c;
-        *out = make_float2(s, q);
-    }
-}
-
-__global__ void __launch_bounds__(128)
-gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                   int B, int HW, int C, int groups, int nchunk, float eps) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= B * groups) return;
-    const int b = warp / groups, g = warp % groups;
+gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ scale, float* __restrict__ shift, int HW, int C, int groups, float eps) {
+    const int b = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
-    const float2* p = reinterpret_cast<const float2*>(partial) + (size_t)b * nchunk * C + g * cpg;
-    double s = 0.0, q = 0.0;
-    const int items = nchunk * cpg;
-    for (int it = lane; it < items; it += 32) {
-        const int ch = it / cpg, cc = it % cpg;
-        const float2 v = p[(size_t)ch * C + cc];
-        s += (double)v.x;
-        q += (double)v.y;
+    const int total = HW * cpg;
+    const float* xb = x + (size_t)b * HW * C + g * cpg;
+    float s = 0.f, q = 0.f;
+    int e = threadIdx.x;
+    // 4 independent loads in flight per thread
+    for (; e + 3 * 256 < total; e += 4 * 256) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ee = e + u * 256;
+            const int p = ee / cpg, cc = ee - p * cpg;
+            v[u] = xb[(size_t)p * C + cc];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s += v[u];
+            q = fmaf(v[u], v[u], q);
+        }
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    const double n = (double)HW * (double)cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float fmean = (float)mean;
-    for (int cc = lane; cc < cpg; cc += 32) {
+    for (; e < total; e += 256) {
+        const int p = e / cpg, cc = e - p * cpg;
+        const float v = xb[(size_t)p * C + cc];
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    double ds = warp_sum((double)s), dq = warp_sum((double)q);
+    __shared__ double red[2][8];
+    __shared__ float stat[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[0][warp] = ds;
+        red[1][warp] = dq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            ts += red[0][w];
+            tq += red[1][w];
+        }
+        const double n = (double)total;
+        const double mean = ts / n;
+        double var = tq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[0] = (float)mean;
+        stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float fmean = stat[0], rstd = stat[1];
+    for (int cc = threadIdx.x; cc < cpg; cc += 256) {
         const int c = g * cpg + cc;
         const float ga = gamma != nullptr ? gamma[c] : 1.f;
         const float be = beta != nullptr ? beta[c] : 0.f;
@@ -96,33 +102,23 @@ affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
     }
 }
 
-inline int gn_chunks(int HW) { return ceil_div(HW, GN_PIX); }
-
 }  // namespace
 }  // namespace afldm
 
 using namespace afldm;
 
-extern "C" size_t afldm_groupnorm_scratch_floats(int B, int HW, int C) {
-    if (B <= 0 || HW <= 0 || C <= 0) return 0;
-    return (size_t)B * gn_chunks(HW) * C * 2;
-}
+extern "C" size_t afldm_groupnorm_scratch_floats(int, int, int) { return 0; }
 
 extern "C" int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, int groups, float eps,
                                           const float* gamma, const float* beta, float* scale,
-                                          float* shift, float* partial, afldm_stream_t stream) {
-    if (x == nullptr || scale == nullptr || shift == nullptr || partial == nullptr) return AFLDM_E_ARG;
+                                          float* shift, float* /*partial: unused in this build*/,
+                                          afldm_stream_t stream) {
+    if (x == nullptr || scale == nullptr || shift == nullptr) return AFLDM_E_ARG;
     if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0) return AFLDM_E_ARG;
     if (C % groups != 0) return AFLDM_E_SHAPE;
-    if ((reinterpret_cast<uintptr_t>(partial) & 7u) != 0) return AFLDM_E_ARG;
-    cudaStream_t st = as_stream(stream);
-    const int nchunk = gn_chunks(HW);
-    const int threads = C >= 256 ? 256 : ((C + 31) / 32) * 32;
-    gn_partial_kernel<<<dim3(nchunk, B), threads, 0, st>>>(x, partial, HW, C, nchunk);
-    const int warps = B * groups;
-    gn_finalize_kernel<<<ceil_div(warps, 4), 128, 0, st>>>(partial, gamma, beta, scale, shift, B, HW, C,
-                                                          groups, nchunk, eps);
-    return launched(2);
+    if ((long long)HW * (C / groups) > 0x7fffffffLL) return AFLDM_E_SHAPE;
+    gn_stats_kernel<<<B * groups, 256, 0, as_stream(stream)>>>(x, gamma, beta, scale, shift, HW, C, groups, eps);
+    return launched();
 }
 
 extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,

@@ -168,11 +168,12 @@ def groupnorm_affine(x: torch.Tensor, groups: int, eps: float, gamma: Optional[t
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
     L = _lib.lib()
-    part = scratch(x.device, L.afldm_groupnorm_scratch_floats(b, hw, c))
+    need = L.afldm_groupnorm_scratch_floats(b, hw, c)
+    part = scratch(x.device, need) if need else None
     ss = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
     _run("groupnorm_affine", dict(B=b, HW=hw, C=c, elems=x.numel()),
          lambda: L.afldm_groupnorm_affine_f32(x.data_ptr(), b, hw, c, groups, float(eps), _ptr(gamma), _ptr(beta),
-                                              ss[0].data_ptr(), ss[1].data_ptr(), part.data_ptr(), _stream()),
+                                              ss[0].data_ptr(), ss[1].data_ptr(), _ptr(part), _stream()),
          (x, gamma, beta, ss, part))
     return ss[0], ss[1]
 
@@ -275,7 +276,7 @@ def linear_rows(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 
 # ------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, algo: Optional[str] = None) -> torch.Tensor:
     """softmax(q k^T / sqrt(d)) v per head.  q [B,Nq,heads*d], k/v [Bkv,Nk,heads*d]; each may be a
     column slice of a wider (e.g. fused QKV) buffer.  B % Bkv == 0: batch b uses K/V batch b // (B/Bkv)."""
     b, nq, cd = q.shape
@@ -289,9 +290,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
     if out is None:
         out = torch.empty((b, nq, cd), dtype=torch.float32, device=q.device)
     L = _lib.lib()
-    _run("attention", dict(B=b, Nq=nq, Nk=nk, heads=heads, d=d, flops=4.0 * b * heads * nq * nk * d),
+    # precision class follows the convolution path: 'tf32' -> tensor-core products, 'simt' -> exact fp32
+    a = CONV_ALGO[algo or _default_conv_algo] if d % 8 == 0 else 0
+    _run("attention_tf32" if a else "attention", dict(B=b, Nq=nq, Nk=nk, heads=heads, d=d, flops=4.0 * b * heads * nq * nk * d),
          lambda: L.afldm_attention_f32(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1),
-                                       out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, _stream()),
+                                       out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, a, _stream()),
          (q, k, v, out))
     return out
 

@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--conv-algo", default=os.environ.get("AFLDM_CONV_ALGO", "tf32"), choices=["simt", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--dump-breakdown", default=None, help="write the per-shape kernel timing table (CSV) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -291,6 +292,14 @@ def main():
                 a["bytes"] += count * 20.0 * meta["elems"]
             elif name == "lpf_down2":
                 a["bytes"] += count * 5.0 * meta["elems"]
+        if args.dump_breakdown:
+            with open(args.dump_breakdown, "w") as f:
+                f.write("kernel,count,us_each,us_total,tflops_or_gbs,meta\n")
+                for (name, _key), (count, ms_each, meta, _n) in sorted(table.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+                    rate = meta.get("flops", 0.0) / (ms_each / 1e3) / 1e12 if meta.get("flops") else \
+                        8.0 * meta.get("elems", 0) / (ms_each / 1e3) / 1e9
+                    f.write(f"{name},{count},{ms_each * 1e3:.1f},{count * ms_each * 1e3:.1f},{rate:.1f},"
+                            f"\"{json.dumps(meta)}\"\n")
         total_iso = sum(a["ms"] for a in agg.values())
         breakdown = {k: {"launches": v["launches"], "ms_per_step": round(v["ms"], 4),
                          "share": round(v["ms"] / total_iso, 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}

@@ -43,6 +43,7 @@ enum {
 
 enum { AFLDM_ACT_IDENTITY = 0, AFLDM_ACT_SILU = 1 };
 enum { AFLDM_CONV_SIMT_F32 = 0, AFLDM_CONV_TCGEN05_TF32 = 1 };
+enum { AFLDM_ATTN_SIMT_F32 = 0, AFLDM_ATTN_MMA_TF32 = 1 };
 
 /* Library / build identification. abi = 1. */
 AFLDM_API int afldm_abi_version(void);
@@ -80,7 +81,8 @@ AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W,
  * torch.nn.GroupNorm(groups, C, eps) as used by diffusers ResnetBlock2D / Attention
  * (SURVEY.md 8a-R).  Produces the folded per-(b,c) affine  y = x*scale + shift :
  *   scale[b,c] = gamma[c]*rstd[b,g],  shift[b,c] = beta[c] - mean[b,g]*gamma[c]*rstd[b,g].
- * x NHWC [B,HW,C].  `partial` is caller scratch of afldm_groupnorm_scratch_floats(B,HW,C) floats. */
+ * x NHWC [B,HW,C].  `partial` is caller scratch of afldm_groupnorm_scratch_floats(B,HW,C) floats
+ * (0 in this build: one CTA per (b, group) reduces in a single launch; NULL is accepted). */
 AFLDM_API size_t afldm_groupnorm_scratch_floats(int B, int HW, int C);
 AFLDM_API int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, int groups, float eps,
                                const float* gamma, const float* beta,
@@ -123,10 +125,13 @@ AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float*
  * cross-frame K/V source of afldm/pipelines/cross_frame_attn.py:79-97:
  *   q [B][Nq][heads*d] (row pitch q_pitch), k/v [Bkv][Nk][heads*d] (row pitch kv_pitch),
  *   batch b reads K/V batch  b / (B / Bkv)  (repeat semantics of :91-97), scale = d^-0.5,
- *   o [B][Nq][heads*d] (row pitch o_pitch).  d % 4 == 0, d <= 64 in this build. */
+ *   o [B][Nq][heads*d] (row pitch o_pitch).  d % 4 == 0, d <= 64 in this build.
+ * algo: AFLDM_ATTN_SIMT_F32 = exact fp32 FMA (the reference's fp32 SDPA class);
+ *       AFLDM_ATTN_MMA_TF32 = tensor-core products on TF32 operands (d % 8 == 0), fp32 accumulation
+ *       and fp32 online softmax - used together with the TF32 convolution path. */
 AFLDM_API int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
                         float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
-                        afldm_stream_t stream);
+                        int algo, afldm_stream_t stream);
 
 /* In-place row softmax: x[r][:] = softmax(scale * x[r][:]) over `cols` entries, row pitch `pitch`.
  * Used by the large-head-dim attention (VAE mid block: 1 head of 512) which runs as

@@ -196,23 +196,47 @@ def test_conv2d_split_k_is_deterministic():
 def test_attention_vs_sdpa(b, bkv, nq, nk, heads, d):
     c = heads * d
     q, k, v = randn(b, nq, c, seed=1), randn(bkv, nk, c, seed=2), randn(bkv, nk, c, seed=3)
-    got = ops.attention(q, k, v, heads)
+    got = ops.attention(q, k, v, heads, algo="simt")
     rep = b // bkv
     kk = k.unsqueeze(1).repeat(1, rep, 1, 1).reshape(b, nk, c)          # cross_frame_attn.py:91-97
     vv = v.unsqueeze(1).repeat(1, rep, 1, 1).reshape(b, nk, c)
     sp = lambda t, n: t.view(b, n, heads, d).transpose(1, 2)
     want = F.scaled_dot_product_attention(sp(q, nq), sp(kk, nk), sp(vv, nk)).transpose(1, 2).reshape(b, nq, c)
     torch.testing.assert_close(got, want, rtol=0, atol=2e-5)
+    if d % 8 == 0:
+        # tensor-core variant: TF32 products (10-bit mantissa), fp32 softmax / accumulation
+        tc = ops.attention(q, k, v, heads, algo="tf32")
+        err = (tc - want).abs()
+        assert err.max().item() < 6e-3 and err.mean().item() < 6e-4, (err.max().item(), err.mean().item())
+
+
+def test_attention_tf32_exact_on_tf32_representable_inputs():
+    """With inputs exactly representable in TF32 and a one-hot softmax the tensor-core kernel must
+    return the selected V rows exactly: checks fragment layouts / key permutation, not rounding."""
+    b, n, heads, d = 2, 192, 3, 24
+    c = heads * d
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(0)).to(DEV)
+    basis = torch.zeros(n, d, device=DEV)
+    basis[torch.arange(n, device=DEV), torch.arange(n, device=DEV) % d] = 1.0
+    code = ((torch.arange(n, device=DEV)[:, None] >> torch.arange(d, device=DEV)[None, :]) & 1).float() * 2 - 1  # +-1 codes
+    k = (code * 64.0).repeat(1, heads).expand(b, n, c).contiguous()              # key j = 64 * code(j)
+    q = (code[idx] * 64.0).repeat(1, heads).expand(b, n, c).contiguous()         # query i matches key idx[i]
+    v = ((randn(b, n, c, seed=5) * 16).round() / 16)
+    out = ops.attention(q, k, v, heads, algo="tf32")
+    torch.testing.assert_close(out, v[:, idx], rtol=0, atol=1e-6)
 
 
 def test_attention_on_fused_qkv_slices():
     b, n, heads, d = 2, 64, 4, 24
     c = heads * d
     qkv = randn(b, n, 3 * c, seed=4)
-    got = ops.attention(qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:], heads)
+    got = ops.attention(qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:], heads, algo="simt")
     sp = lambda t: t.reshape(b, n, heads, d).transpose(1, 2)
     want = F.scaled_dot_product_attention(sp(qkv[:, :, :c]), sp(qkv[:, :, c:2 * c]), sp(qkv[:, :, 2 * c:]))
-    torch.testing.assert_close(got, want.transpose(1, 2).reshape(b, n, c), rtol=0, atol=2e-5)
+    want = want.transpose(1, 2).reshape(b, n, c)
+    torch.testing.assert_close(got, want, rtol=0, atol=2e-5)
+    tc = ops.attention(qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:], heads, algo="tf32")
+    assert (tc - want).abs().max().item() < 6e-3
 
 
 def test_attention_large_head_dim_via_gemm():
