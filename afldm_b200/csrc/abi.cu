@@ -1,10 +1,18 @@
 // Library identification, launch accounting and error strings of the afldm_b200 C ABI.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace afldm {
 static std::atomic<unsigned long long> g_launches{0};
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("AFLDM_PDL");
+        return e != nullptr && e[0] == '1';   // opt-in: measured neutral under CUDA-graph replay (profiles/r01)
+    }();
+    return on;
+}
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace afldm
 

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
                  const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                  int Bkv_rep, int Nq, int Nk, float qscale) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int D4 = D / 4;
     __shared__ float4 Ks[ATT_KT * D4];
     __shared__ float4 Vs[ATT_KT * D4];
@@ -120,6 +122,8 @@ attention_kernel(const float* __restrict__ q, int q_pitch, const float* __restri
 // x[r][:] = softmax(scale * x[r][:]); one warp per row, row kept in registers when cols <= 1024.
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(float* __restrict__ x, long long rows, int cols, int pitch, float scale_log2e) {
+    pdl_trigger();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -163,6 +167,8 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
                      const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                      int Bkv_rep, int Nq, int Nk, float qscale) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int KT = 64;            // keys per tile
     constexpr int P = D + 4;          // smem row pitch (words)
     constexpr int DK = D / 8;         // k-steps of Q.K^T == n-tiles of P.V
@@ -286,7 +292,7 @@ template <int D>
 int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
                int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
     const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
-    attention_mma_kernel<D><<<dim3(ceil_div(Nq, 64), heads, B), 128, 0, st>>>(
+    launch_k(attention_mma_kernel<D>, dim3(ceil_div(Nq, 64), heads, B), dim3(128), 0, st, 
         q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
     return launched();
 }
@@ -296,7 +302,7 @@ int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_p
            int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
     const int threads = Nq >= ATT_THREADS ? ATT_THREADS : ((Nq + 31) / 32) * 32;
     const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
-    attention_kernel<D><<<dim3(ceil_div(Nq, threads), heads, B), threads, 0, st>>>(
+    launch_k(attention_kernel<D>, dim3(ceil_div(Nq, threads), heads, B), dim3(threads), 0, st, 
         q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
     return launched();
 }
@@ -311,7 +317,7 @@ extern "C" int afldm_softmax_rows_f32(float* x, long long rows, int cols, int pi
     if (x == nullptr || rows <= 0 || cols <= 0 || pitch < cols) return AFLDM_E_ARG;
     const long long blocks = (rows + 7) / 8;
     if (blocks > 0x7fffffffLL) return AFLDM_E_SHAPE;
-    softmax_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, rows, cols, pitch,
+    launch_k(softmax_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, rows, cols, pitch,
                                                                          scale * 1.4426950408889634f);
     return launched();
 }

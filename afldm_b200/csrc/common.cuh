@@ -20,6 +20,34 @@ inline int launched(int n = 1) {
     return (int)cudaGetLastError();
 }
 
+// Programmatic dependent launch (PDL): every kernel of this library starts with pdl_wait(), so it may be
+// launched while its predecessor on the stream is still draining - launch latency and the prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap the previous kernel's tail.  Works under
+// CUDA-graph capture (programmatic edges).  Opt-in with AFLDM_PDL=1.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface via cudaGetLastError()
+}
+
+#ifdef __CUDACC__
+// Block until every prerequisite grid has completed and its writes are visible (no-op without PDL).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Allow the next kernel on the stream to start launching.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 inline cudaStream_t as_stream(afldm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

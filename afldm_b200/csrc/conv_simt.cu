@@ -57,6 +57,8 @@ struct ConvArgs {
 // FAST: Cin % 16 == 0, x_pitch % 4 == 0, x and w 16-byte aligned -> float4 loads, one tap per chunk.
 template <bool FAST>
 __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][CBK][LDA];
     __shared__ __align__(16) float Bs[2][CBK][LDB];
     const int tid = threadIdx.x;
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splitk, const float* __restrict__ bias,
                      const float* __restrict__ row_add, int row_add_pitch, const float* residual,
                      int res_pitch, float* y, int y_pitch, int M, int Cout, int HW) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)M * Cout;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -222,7 +226,7 @@ void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const 
                           int HW, cudaStream_t st) {
     const long long total = (long long)M * Cout;
     const int blocks = (int)std::min<long long>(148 * 4, (total + 255) / 256);
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(ws, splitk, bias, row_add, row_add_pitch, residual, res_pitch, y,
+    launch_k(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, splitk, bias, row_add, row_add_pitch, residual, res_pitch, y,
                                                  y_pitch,
                                                  M, Cout, HW);
 }
@@ -243,9 +247,9 @@ int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* b
     const bool fast = (Cin % 16 == 0) && (x_pitch % 4 == 0) && aligned16(x) && aligned16(w);
     dim3 grid(p.mtiles, p.ntiles, p.splitk);
     if (fast)
-        conv_simt_kernel<true><<<grid, 256, 0, st>>>(a);
+        launch_k(conv_simt_kernel<true>, dim3(grid), dim3(256), 0, st, a);
     else
-        conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);
+        launch_k(conv_simt_kernel<false>, dim3(grid), dim3(256), 0, st, a);
     int launches = 1;
     if (p.splitk > 1) {
         splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, p.M, Cout,

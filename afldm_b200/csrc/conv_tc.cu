@@ -170,10 +170,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    // Everything above touched only this CTA's shared / tensor memory: it may overlap the tail of the
+    // previous kernel on the stream.  From here on global memory is read.
+    pdl_trigger();
+    pdl_wait();
 
     const int m0 = blockIdx.x * TBM;
     const int n0 = blockIdx.y * a.BN;
@@ -291,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        if (n + j >= a.Cout) break;
                         float t = e[j];
                         if (a.bias != nullptr) t += a.bias[n + j];
                         if (a.row_add != nullptr) t += a.row_add[(size_t)(mm / a.HW) * a.row_add_pitch + n + j];
@@ -340,7 +349,9 @@ struct TcPlan {
 TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     TcPlan p{};
     p.ok = false;
-    if (Cin % TBK != 0 || Cout % 16 != 0 || !is_pow2(W) || !is_pow2(H)) return p;
+    // Cout < 16 (conv_out: C -> 4 / 3) runs as one BN = 16 tile: the weight box rows past Cout are
+    // zero-filled by TMA and the epilogue masks them.
+    if (Cin % TBK != 0 || (Cout >= 16 && Cout % 16 != 0) || !is_pow2(W) || !is_pow2(H)) return p;
     if (W > TBM && W % TBM != 0) return p;
     p.M = B * H * W;
     p.mtiles = ceil_div(p.M, TBM);
@@ -359,17 +370,19 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     static const int force_bn = getenv("AFLDM_TC_BN") ? atoi(getenv("AFLDM_TC_BN")) : 0;
     static const int force_split = getenv("AFLDM_TC_SPLITK") ? atoi(getenv("AFLDM_TC_SPLITK")) : 0;
     static const int force_stages = getenv("AFLDM_TC_STAGES") ? atoi(getenv("AFLDM_TC_STAGES")) : 0;
-    const int cands[] = {256, 192, 128, 96, 64, 32};
-    int best = 0;
-    for (int bn : cands) {
-        if (bn > Cout && bn != 32) continue;
-        if (Cout % bn != 0 && bn > 64) continue;
-        const int tiles = p.mtiles * ceil_div(Cout, bn);
-        if (tiles >= 120) { best = bn; break; }
-    }
-    if (best == 0) best = Cout >= 64 ? 64 : (Cout >= 32 ? 32 : 16);
+    // Tile width, from a sweep on B200 (profiles/r01_conv_bn_sweep.md).  The main loop is bound by
+    // L2 -> SMEM operand traffic and by per-CTA prologue / epilogue latency, so the best width is the one
+    // that puts two CTAs on every SM (one CTA's epilogue hides behind the other's main loop): 96 columns
+    // when the grid is large, 64 for the 16x16 level and for 1x1 layers, 96 again for K-heavy small-M layers.
+    int best;
+    if (Cout < 64) best = Cout >= 32 ? 32 : 16;
+    else if (Cout % 96 == 0 && (p.mtiles * (Cout / 96) >= 222 || (p.mtiles <= 8 && ks == 3))) best = 96;
+    else if (Cout % 64 == 0) best = (Cout % 128 == 0 && p.mtiles * (Cout / 128) >= 296) ? 128 : 64;
+    else if (Cout % 96 == 0) best = 96;
+    else best = 32;
     if (force_bn > 0 && force_bn % 16 == 0 && force_bn <= 256 && (Cout % force_bn == 0 || force_bn <= 64)) best = force_bn;
     if (best > Cout) best = Cout;        // Cout in {16, 32, 48}: one narrow tile
+    if (best < 16) best = 16;
     p.BN = best;
     p.ntiles = ceil_div(Cout, p.BN);
     const int tiles = p.mtiles * p.ntiles;
@@ -380,6 +393,7 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
         s = std::min(s, 64);
     }
     if (force_split > 0) s = std::min(force_split, p.total_iters);
+    if (Cout % 4 != 0) s = 1;            // split-K partials are written as float4
     p.iters_per_split = ceil_div(p.total_iters, s);
     p.splitk = ceil_div(p.total_iters, p.iters_per_split);
     const int stage_bytes = A_STAGE_BYTES + p.BN * TBK * 4;
@@ -455,11 +469,11 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.iters_per_split = p.iters_per_split;
     a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
-    a.vec_ok = ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
+    a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
     dim3 grid(p.mtiles, p.ntiles, p.splitk);
-    conv_tc_kernel<<<grid, TC_THREADS, p.smem_bytes, st>>>(map_a, map_b, a);
+    launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
     int launches = 1;
     if (p.splitk > 1) {
         splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch,

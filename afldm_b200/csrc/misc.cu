@@ -17,6 +17,8 @@ template <int ACT_IN, int ACT_OUT>
 __global__ void __launch_bounds__(256)
 linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ y, int M, int K, int N) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float xs[];  // [M][K]
     for (int i = threadIdx.x; i < M * K; i += blockDim.x) xs[i] = apply_act<ACT_IN>(x[i]);
     __syncthreads();
@@ -48,6 +50,8 @@ linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 
 // ------------------------------------------------------------------ timestep embedding
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim) {
+    pdl_trigger();
+    pdl_wait();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -63,6 +67,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 __global__ void __launch_bounds__(256)
 concat_kernel(const float4* __restrict__ a, int Ca4, const float4* __restrict__ b, int Cb4,
               float4* __restrict__ y, long long total4) {
+    pdl_trigger();
+    pdl_wait();
     const int C4 = Ca4 + Cb4;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
@@ -76,6 +82,8 @@ concat_kernel(const float4* __restrict__ a, int Ca4, const float4* __restrict__ 
 // in [B][R][S] -> out [B][S][R]  (NCHW->NHWC: R = C, S = HW; NHWC->NCHW: R = HW, S = C)
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int S) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float t[32][33];
     const int b = blockIdx.z;
     const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -99,6 +107,8 @@ transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, i
 __global__ void __launch_bounds__(256)
 axpby_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out, float cx,
              float ce, long long n) {
+    pdl_trigger();
+    pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = fmaf(cx, x[i], ce * e[i]);
@@ -107,6 +117,8 @@ axpby_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __
 __global__ void __launch_bounds__(256)
 axpby_dev_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out,
                  const float* __restrict__ coef, long long n) {
+    pdl_trigger();
+    pdl_wait();
     const float cx = coef[0], ce = coef[1];
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -121,6 +133,8 @@ __global__ void __launch_bounds__(256)
 upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y,
                  int H, int W, int fh, int fw, int upx, int upy, int downx, int downy, int padx0, int pady0,
                  int outH, int outW, int flip, float gain, long long total) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ox = (int)(i % outW);
@@ -169,7 +183,7 @@ extern "C" int afldm_linear_rows_f32(const float* x, const float* w, const float
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
             if (e != cudaSuccess) return (int)e;                                                       \
         }                                                                                              \
-        kern<<<blocks, 256, smem, st>>>(x, w, bias, y, M, K, N);                                       \
+        launch_k(kern, dim3(blocks), dim3(256), smem, st, x, w, bias, y, M, K, N);                                       \
         return launched();                                                                             \
     }
     const bool ai = act_in == AFLDM_ACT_SILU, ao = act_out == AFLDM_ACT_SILU;
@@ -187,7 +201,7 @@ extern "C" int afldm_timestep_embedding_f32(const float* t, float* out, int B, i
     if (t == nullptr || out == nullptr || B <= 0 || dim <= 0) return AFLDM_E_ARG;
     if (dim % 2 != 0) return AFLDM_E_SHAPE;
     const int n = B * (dim / 2);
-    timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(t, out, B, dim);
+    launch_k(timestep_embedding_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, as_stream(stream), t, out, B, dim);
     return launched();
 }
 
@@ -197,7 +211,7 @@ extern "C" int afldm_concat_channels_f32(const float* a, int Ca, const float* b,
     if (Ca % 4 != 0 || Cb % 4 != 0) return AFLDM_E_SHAPE;
     if (!aligned16(a) || !aligned16(b) || !aligned16(y)) return AFLDM_E_ARG;
     const long long total4 = pixels * (Ca + Cb) / 4;
-    concat_kernel<<<grid_for(total4), 256, 0, as_stream(stream)>>>(
+    launch_k(concat_kernel, dim3(grid_for(total4)), dim3(256), 0, as_stream(stream), 
         reinterpret_cast<const float4*>(a), Ca / 4, reinterpret_cast<const float4*>(b), Cb / 4,
         reinterpret_cast<float4*>(y), total4);
     return launched();
@@ -206,7 +220,7 @@ extern "C" int afldm_concat_channels_f32(const float* a, int Ca, const float* b,
 static int transpose_launch(const float* x, float* y, int B, int R, int S, afldm_stream_t stream) {
     if (x == nullptr || y == nullptr || B <= 0 || R <= 0 || S <= 0 || x == y) return AFLDM_E_ARG;
     if (B > 65535 || ceil_div(R, 32) > 65535) return AFLDM_E_SHAPE;
-    transpose_kernel<<<dim3(ceil_div(S, 32), ceil_div(R, 32), B), 256, 0, as_stream(stream)>>>(x, y, R, S);
+    launch_k(transpose_kernel, dim3(ceil_div(S, 32), ceil_div(R, 32), B), dim3(256), 0, as_stream(stream), x, y, R, S);
     return launched();
 }
 
@@ -221,14 +235,14 @@ extern "C" int afldm_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, in
 extern "C" int afldm_axpby_f32(const float* x, const float* eps, float* out, float cx, float ce, long long n,
                                afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || n <= 0) return AFLDM_E_ARG;
-    axpby_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, eps, out, cx, ce, n);
+    launch_k(axpby_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, eps, out, cx, ce, n);
     return launched();
 }
 
 extern "C" int afldm_axpby_dev_f32(const float* x, const float* eps, float* out, const float* coef,
                                    long long n, afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || coef == nullptr || n <= 0) return AFLDM_E_ARG;
-    axpby_dev_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, eps, out, coef, n);
+    launch_k(axpby_dev_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, eps, out, coef, n);
     return launched();
 }
 
@@ -243,7 +257,7 @@ extern "C" int afldm_upfirdn2d_f32(const float* x, const float* f, float* y, int
     if (outW < 1 || outH < 1) return AFLDM_E_SHAPE;
     const long long total = (long long)B * C * outH * outW;
     const int blocks = (int)((total + 255) / 256);
-    upfirdn2d_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, f, y, H, W, fh, fw, upx, upy, downx, downy, padx0,
+    launch_k(upfirdn2d_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, f, y, H, W, fh, fw, upx, upy, downx, downy, padx0,
                                                            pady0, outH, outW, flip, gain, total);
     return launched();
 }

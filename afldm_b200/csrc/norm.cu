@@ -17,6 +17,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ scale, float* __restrict__ shift, int HW, int C, int groups, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
     const int total = HW * cpg;
@@ -82,6 +84,8 @@ template <int ACT>
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, int C4,
                   long long per_image4, const float4* __restrict__ scale, const float4* __restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 v = x[i];
@@ -117,7 +121,7 @@ extern "C" int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, 
     if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0) return AFLDM_E_ARG;
     if (C % groups != 0) return AFLDM_E_SHAPE;
     if ((long long)HW * (C / groups) > 0x7fffffffLL) return AFLDM_E_SHAPE;
-    gn_stats_kernel<<<B * groups, 256, 0, as_stream(stream)>>>(x, gamma, beta, scale, shift, HW, C, groups, eps);
+    launch_k(gn_stats_kernel, dim3(B * groups), dim3(256), 0, as_stream(stream), x, gamma, beta, scale, shift, HW, C, groups, eps);
     return launched();
 }
 
@@ -134,10 +138,10 @@ extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int
     auto sc = reinterpret_cast<const float4*>(scale);
     auto sh = reinterpret_cast<const float4*>(shift);
     if (act == AFLDM_ACT_SILU)
-        affine_act_kernel<AFLDM_ACT_SILU><<<blocks, 256, 0, st>>>(
+        launch_k(affine_act_kernel<AFLDM_ACT_SILU>, dim3(blocks), dim3(256), 0, st, 
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh);
     else if (act == AFLDM_ACT_IDENTITY)
-        affine_act_kernel<AFLDM_ACT_IDENTITY><<<blocks, 256, 0, st>>>(
+        launch_k(affine_act_kernel<AFLDM_ACT_IDENTITY>, dim3(blocks), dim3(256), 0, st, 
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh);
     else
         return AFLDM_E_ARG;

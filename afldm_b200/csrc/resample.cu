@@ -20,6 +20,7 @@
 // Algorithmic HBM traffic: filtered_act 8 B/element, up2 20 B per input element,
 // lpf_down2 5 B per input element (fp32).
 #include "common.cuh"
+#include "resample.cuh"
 #include "taps.inc"
 
 namespace afldm {
@@ -77,6 +78,8 @@ template <int N, int CG, int MODE, int ACT>
 __global__ void __launch_bounds__(256, 2)
 resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
                 const float* __restrict__ scale, const float* __restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float tile[];
     constexpr int PITCH = Tile<N, CG>::PITCH;
     constexpr int M = 2 * N;
@@ -172,7 +175,7 @@ int launch_one(const float* x, float* y, int B, int C, const float* scale, const
     }
     constexpr int tasks = 2 * N * CG;
     const int threads = tasks >= 256 ? 256 : (tasks < 32 ? 32 : tasks);
-    kern<<<dim3(C / CG, B), threads, smem, st>>>(x, y, C, scale, shift);
+    launch_k(kern, dim3(C / CG, B), dim3(threads), smem, st, x, y, C, scale, shift);
     return launched();
 }
 
@@ -200,27 +203,41 @@ bool bad_args(const float* x, const float* y, int B, int H, int W, int C, const 
 
 using namespace afldm;
 
+extern "C" size_t afldm_resample_workspace_floats(int op, int B, int H, int W, int C) {
+    if (op < 0 || op > 2 || B <= 0 || H <= 0 || W <= 0 || C <= 0 || H != W) return 0;
+    return resample_large_workspace_floats(op, B, H, C);   // 0 for the planes that run fused in one kernel
+}
+
 extern "C" int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int W, int C, int act,
-                                      const float* scale, const float* shift, afldm_stream_t stream) {
+                                      const float* scale, const float* shift, float* workspace,
+                                      size_t workspace_floats, afldm_stream_t stream) {
     if (bad_args(x, y, B, H, W, C, scale, shift)) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
     if (H != W) return AFLDM_E_SHAPE;  // the reference's mask is built from W only (ideal_lpf.py:81-88)
     cudaStream_t st = as_stream(stream);
+    if (H > 32) return resample_large(MODE_FACT, act, x, y, B, H, C, scale, shift, workspace, workspace_floats, st);
     if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, scale, shift, st);
-    if (act == AFLDM_ACT_IDENTITY)
-        return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
-    return AFLDM_E_ARG;
+    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
 }
 
 extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
-                                   const float* scale, const float* shift, afldm_stream_t stream) {
+                                   const float* scale, const float* shift, float* workspace,
+                                   size_t workspace_floats, afldm_stream_t stream) {
     if (bad_args(x, y, B, H, W, C, scale, shift) || x == y) return AFLDM_E_ARG;
     if (H != W) return AFLDM_E_SHAPE;
-    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, as_stream(stream));
+    cudaStream_t st = as_stream(stream);
+    if (H > 32)
+        return resample_large(MODE_UP2, AFLDM_ACT_IDENTITY, x, y, B, H, C, scale, shift, workspace, workspace_floats, st);
+    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
 }
 
-extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C,
-                                   afldm_stream_t stream) {
+extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,
+                                   size_t workspace_floats, afldm_stream_t stream) {
     if (bad_args(x, y, B, H, W, C, nullptr, nullptr) || x == y) return AFLDM_E_ARG;
     if (H != W) return AFLDM_E_SHAPE;
-    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, nullptr, nullptr, as_stream(stream));
+    cudaStream_t st = as_stream(stream);
+    if (H > 32)
+        return resample_large(MODE_DOWN2, AFLDM_ACT_IDENTITY, x, y, B, H, C, nullptr, nullptr, workspace,
+                              workspace_floats, st);
+    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, nullptr, nullptr, st);
 }

@@ -128,9 +128,12 @@ def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: O
     if out is None:
         out = torch.empty_like(x)
     L = _lib.lib()
+    need = L.afldm_resample_workspace_floats(0, b, h, w, c)
+    ws = scratch(x.device, need) if need else None
     _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel()),
          lambda: L.afldm_filtered_act_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act],
-                                          _ptr(scale), _ptr(shift), _stream()), (x, out, scale, shift))
+                                          _ptr(scale), _ptr(shift), _ptr(ws), need, _stream()),
+         (x, out, scale, shift, ws))
     return out
 
 
@@ -141,9 +144,11 @@ def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
     b, h, w, c = x.shape
     out = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
     L = _lib.lib()
+    need = L.afldm_resample_workspace_floats(1, b, h, w, c)
+    ws = scratch(x.device, need) if need else None
     _run("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel()),
          lambda: L.afldm_up2_ideal_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, _ptr(scale), _ptr(shift),
-                                       _stream()), (x, out, scale, shift))
+                                       _ptr(ws), need, _stream()), (x, out, scale, shift, ws))
     return out
 
 
@@ -155,8 +160,11 @@ def lpf_down2(x: torch.Tensor) -> torch.Tensor:
         raise _lib.AfldmError("lpf_down2: even input size expected")
     out = torch.empty((b, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
     L = _lib.lib()
+    need = L.afldm_resample_workspace_floats(2, b, h2 // 2, w2 // 2, c)
+    ws = scratch(x.device, need) if need else None
     _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel()),
-         lambda: L.afldm_lpf_down2_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _stream()), (x, out))
+         lambda: L.afldm_lpf_down2_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _ptr(ws), need,
+                                       _stream()), (x, out, ws))
     return out
 
 

@@ -147,9 +147,10 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- per-kernel timing
-def time_records(records, torch, reps=5):
-    """Re-issue every recorded C call in isolation and time it with CUDA events on the launch stream.
-    Returns {(name, key): [count, total_ms_per_step, meta]}."""
+def time_records(records, torch, reps=10):
+    """Device time of every distinct recorded C call: `reps` back-to-back launches are captured in a CUDA
+    graph and the replay is timed with CUDA events (no host launch gaps inside the timed region).
+    Returns {(name, key): [count, ms_per_launch, meta, name]}."""
     table = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for name, meta, fn, _keep in records:
@@ -159,13 +160,18 @@ def time_records(records, torch, reps=5):
             ent[0] += 1
             continue
         fn()
-        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
         ev0.record()
-        for _ in range(reps):
-            fn()
+        g.replay()
         ev1.record()
         ev1.synchronize()
         table[key] = [1, ev0.elapsed_time(ev1) / reps, meta, name]
+        del g
     return table
 
 

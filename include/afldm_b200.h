@@ -59,23 +59,30 @@ AFLDM_API const char* afldm_error_string(int code);
  * (afldm/af_libs/ideal_lpf.py:12-49 masks, :69-93, :112-134, :148-158).  The taps d, g are
  * baked into the library for n in {2,4,8,16,32,64,128} (afldm_b200/csrc/gen_taps.py).
  * Planes must be square (the reference builds its mask from the last dim only,
- * ideal_lpf.py:81-88) and C a multiple of 32. */
+ * ideal_lpf.py:81-88) and C a multiple of 32.  Planes up to 32 x 32 run fused in one kernel; 64 and
+ * 128 run as three line passes with fp32 intermediates in `workspace`
+ * (afldm_resample_workspace_floats(op, ...) floats; op: 0 filtered act, 1 up2, 2 lpf_down2 with
+ * H, W the sizes of the SMALL plane; 0 when no workspace is needed, NULL is then accepted). */
+AFLDM_API size_t afldm_resample_workspace_floats(int op, int B, int H, int W, int C);
 
 /* WarpedNonlinearity.forward (afldm/af_modules/af_blocks.py:19-28) for 4-D input:
  *   y = LPF(act(Up2(x * scale + shift)))[::2, ::2]   per (b, c) plane,
  * scale/shift are optional per-(b,c) vectors [B*C] (GroupNorm folded in: scale = gamma*rstd,
  * shift = beta - mean*gamma*rstd); pass NULL for none.  x, y: NHWC [B,H,W,C]; may alias. */
 AFLDM_API int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int W, int C, int act,
-                           const float* scale, const float* shift, afldm_stream_t stream);
+                           const float* scale, const float* shift, float* workspace,
+                           size_t workspace_floats, afldm_stream_t stream);
 
 /* UpsampleRFFT(up=2).forward (afldm/af_libs/ideal_lpf.py:148-158), optional affine on load:
  * x NHWC [B,H,W,C] -> y NHWC [B,2H,2W,C]. */
 AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
-                        const float* scale, const float* shift, afldm_stream_t stream);
+                        const float* scale, const float* shift, float* workspace,
+                        size_t workspace_floats, afldm_stream_t stream);
 
 /* LPF_RFFT(0.5)(x)[:, :, ::2, ::2] (afldm/af_modules/af_blocks.py:149-150):
  * x NHWC [B,2H,2W,C] -> y NHWC [B,H,W,C]  (H, W are the OUTPUT sizes). */
-AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, afldm_stream_t stream);
+AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,
+                        size_t workspace_floats, afldm_stream_t stream);
 
 /* ---- GroupNorm ----------------------------------------------------------------------------
  * torch.nn.GroupNorm(groups, C, eps) as used by diffusers ResnetBlock2D / Attention

@@ -167,6 +167,31 @@ def test_cross_frame_attention_store_load():
         assert (a1 - mine(x1, 301).sample).abs().max() == 0
 
 
+def test_afvae_decode_and_encode_vs_oracle():
+    """BASELINE config #3 architecture (configs/vae/model_afvae.json), B = 1: 4x32x32 -> 3x256x256,
+    including the 64 / 128 planes, the d = 512 mid-block attention and the plain-SiLU last block."""
+    from afldm_b200.models import AliasFreeAutoencoderKL
+    torch.manual_seed(0)
+    ref = ON.AutoencoderKL().to(DEV).eval()
+    jitter(ref, 3)
+    mine = AliasFreeAutoencoderKL.from_config().to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    OA.make_af_vae_from_config(ref)
+    z = randn(1, 4, 32, 32, seed=13)
+    with torch.no_grad():
+        want = ref.decode(z / 0.6).sample
+        got = mine.decode(z / 0.6).sample
+        assert got.shape == (1, 3, 256, 256) and got.is_contiguous()
+        err = (got - want).abs().max().item()
+        assert err < 2e-4 * max(1.0, want.abs().max().item()), err
+        assert (mine.decode_scale(z) - got).abs().max() == 0
+        img = randn(1, 3, 64, 64, seed=14)
+        m_want = ref.encode(img).latent_dist.mean
+        m_got = mine.encode(img).latent_dist.mean
+        assert m_got.shape == (1, 4, 8, 8)
+        torch.testing.assert_close(m_got, m_want, rtol=0, atol=2e-4)
+
+
 @pytest.mark.slow
 def test_full_ffhq_unet_step_vs_oracle():
     """BASELINE config #2 architecture (256.4 M parameters), B = 2, one forward."""

@@ -109,6 +109,34 @@ def test_up2_and_lpf_down2_vs_oracle(n, c):
     torch.testing.assert_close(dn, OL.lpf_rfft(y)[:, :, ::2, ::2], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,c,b", [(64, 64, 2), (128, 32, 1), (64, 32, 3)])
+def test_large_plane_resamplers_vs_oracle(n, c, b):
+    """n = 64 / 128 (VAE decoder, 64x64-latent UNets): three line passes through a workspace."""
+    x = randn(b, c, n, n, seed=n + c)
+    torch.testing.assert_close(to_nchw(ops.filtered_act(to_nhwc(x))), OL.filtered_act_fft(x), rtol=0, atol=1e-5)
+    up = to_nchw(ops.up2_ideal(to_nhwc(x)))
+    torch.testing.assert_close(up, OL.upsample_rfft(x), rtol=0, atol=1e-5)
+    torch.testing.assert_close(up[:, :, ::2, ::2], x, rtol=0, atol=0)
+    y = randn(b, c, 2 * n, 2 * n, seed=n + 1)
+    torch.testing.assert_close(to_nchw(ops.lpf_down2(to_nhwc(y))), OL.lpf_rfft(y)[:, :, ::2, ::2], rtol=0, atol=1e-5)
+    # fused GroupNorm affine on the large path
+    gamma, beta = randn(c, seed=1) * 0.2 + 1, randn(c, seed=2) * 0.2
+    xn = to_nhwc(x)
+    scale, shift = ops.groupnorm_affine(xn, 32, 1e-6, gamma, beta)
+    want = OL.filtered_act_fft(F.group_norm(x, 32, gamma, beta, 1e-6))
+    torch.testing.assert_close(to_nchw(ops.filtered_act(xn, scale, shift)), want, rtol=0, atol=2e-5)
+
+
+def test_s64_golden_large_plane(golden):
+    g = golden("ideal_ops")
+    x = torch.from_numpy(g["s64_x"])                           # [1, 3, 64, 64]
+    xs = x.repeat(1, 11, 1, 1)[:, :32].to(DEV)
+    pick = lambda arr: torch.from_numpy(arr).repeat(1, 11, 1, 1)[:, :32].to(DEV)
+    torch.testing.assert_close(to_nchw(ops.up2_ideal(to_nhwc(xs))), pick(g["s64_up2"]), rtol=0, atol=5e-6)
+    torch.testing.assert_close(to_nchw(ops.filtered_act(to_nhwc(xs))), pick(g["s64_filtered_silu"]), rtol=0, atol=5e-6)
+    torch.testing.assert_close(to_nchw(ops.lpf_down2(to_nhwc(xs))), pick(g["s64_lpf_down2"]), rtol=0, atol=5e-6)
+
+
 def test_resampler_linearity_at_full_size():
     """Size-independent property at the BASELINE shape (B=16, 576 ch, 32x32)."""
     a, b = to_nhwc(randn(16, 576, 32, 32, seed=1)), to_nhwc(randn(16, 576, 32, 32, seed=2))
