@@ -130,11 +130,44 @@ def cpu_reference_rate(budget_s: float, steps: int, warmup: int):
     return rate, cores, f"{steps} UNet+DDIM steps of the same workload at sample batch {bs} (rate scaled by {bs}/{BATCH})"
 
 
+def gpu_eager_rate(steps=5, warmup=3):
+    """Extra context for the reference arm (not the contract value): the same oracle model in PyTorch
+    eager on cuda:0 with PyTorch's defaults (cuFFT filters, cuDNN convs with TF32 allowed, fp32 SDPA) - the
+    'reference PyTorch-eager GPU path' that BASELINE.json's 10x target is stated against."""
+    import torch
+    if not torch.cuda.is_available():
+        return None
+    dev = torch.device("cuda", 0)
+    unet, sched = build_oracle_unet()
+    unet = unet.to(dev)
+    sched.set_timesteps(50)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(BATCH, 4, 32, 32, generator=g).to(dev)
+    ts = sched.timesteps.to(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(warmup):
+            x = sched.step(unet(x, ts[i]).sample, int(ts[i]), x, return_dict=False)[0]
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(warmup, warmup + steps):
+            x = sched.step(unet(x, ts[i]).sample, int(ts[i]), x, return_dict=False)[0]
+        ev1.record()
+        ev1.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "oracle UNet + DDIM step, PyTorch eager on cuda:0, fp32 with cuDNN TF32 allowed (PyTorch default)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     rate, cores, sample = cpu_reference_rate(240.0, args.steps, args.warmup)
+    try:
+        eager = gpu_eager_rate()
+    except Exception as e:      # context only: never fail the reference arm on it
+        eager = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
@@ -142,6 +175,7 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "global_batch": BATCH, "where": "host CPU, PyTorch eager fp32"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_eager_context": eager,
     }
     print(json.dumps(line), flush=True)
 
