@@ -33,7 +33,9 @@ SIGNATURES = {
     "afldm_groupnorm_affine_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "afldm_affine_act_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "afldm_conv2d_workspace_floats": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
-    "afldm_conv2d_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "afldm_conv2d_gn_slots": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "afldm_conv2d_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "afldm_groupnorm_finalize_f32": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "afldm_linear_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "afldm_attention_f32": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_softmax_rows_f32": (_i, [_p, _ll, _i, _i, _f, _p]),

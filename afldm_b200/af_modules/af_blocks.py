@@ -60,7 +60,7 @@ class AliasFreeUpsample2D(nn.Module):
         h = ops.up2_ideal(ops.nhwc(hidden_states))
         if self.use_conv:
             w, b, k = conv_params(self.conv)
-            h = ops.conv2d(h, w, b, k)
+            h = ops.conv2d(h, w, b, k, gn_stats=True)       # feeds the next block's GroupNorm (via the skip concat)
         return ops.nchw_view(h)
 
 

@@ -16,16 +16,24 @@ int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* b
                      int y_pitch, int B, int H, int W, int Cin, int Cout, int ks, float* workspace,
                      size_t workspace_floats, cudaStream_t st);
 
+// Rows of one image handled by one CTA of the split-K reduce == pixels per GroupNorm partial slot it emits.
+constexpr int SPLITK_REDUCE_ROWS = 16;
+inline int splitk_reduce_slots(int HW) { return (HW + SPLITK_REDUCE_ROWS - 1) / SPLITK_REDUCE_ROWS; }
+
 // y = sum_z ws[z] + bias + row_add + residual  (fixed summation order: deterministic split-K).
 // Launches one kernel on st (the caller counts it).
 void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const float* row_add,
                           int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int M, int Cout,
-                          int HW, cudaStream_t st);
+                          int HW, float* gn_partial, cudaStream_t st);
 
 // tcgen05 / TMA path.  Returns false (and leaves *floats alone) when the shape is not covered.
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats);
+// Number of GroupNorm partial-sum slots per image the tensor-core path emits for this shape
+// (gn_partial [B][slots][Cout] float2), 0 when it cannot (shape outside the family, ragged tiles).
+int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks);
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,
-                   int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, cudaStream_t st);
+                   int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
+                   cudaStream_t st);
 
 }  // namespace afldm

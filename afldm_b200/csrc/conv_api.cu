@@ -30,18 +30,27 @@ extern "C" size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, in
     return p.splitk > 1 ? (size_t)p.splitk * p.M * Cout : 0;
 }
 
+extern "C" int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
+    if (algo != AFLDM_CONV_TCGEN05_TF32) return 0;
+    return conv_tc_gn_slots(B, H, W, Cin, Cout, ksize);
+}
+
 extern "C" int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
                                 const float* row_add, int row_add_pitch, const float* residual, int res_pitch, float* y,
                                 int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize, int algo,
-                                float* workspace, size_t workspace_floats, afldm_stream_t stream) {
+                                float* workspace, size_t workspace_floats, float* gn_partial,
+                                afldm_stream_t stream) {
     if (conv_bad_args(x, x_pitch, w, y, y_pitch, row_add, row_add_pitch, residual, res_pitch, B, H, W, Cin, Cout, ksize))
         return AFLDM_E_ARG;
     cudaStream_t st = as_stream(stream);
-    if (algo == AFLDM_CONV_SIMT_F32)
+    if (algo == AFLDM_CONV_SIMT_F32) {
+        if (gn_partial != nullptr) return AFLDM_E_ARG;   // statistics are a tensor-core epilogue feature
         return conv_simt_launch(x, x_pitch, w, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Cin,
                                 Cout, ksize, workspace, workspace_floats, st);
+    }
     if (algo == AFLDM_CONV_TCGEN05_TF32)
         return conv_tc_launch(x, x_pitch, w, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Cin,
-                              Cout, ksize, workspace, workspace_floats, st);
+                              Cout, ksize, workspace, workspace_floats, gn_partial, st);
     return AFLDM_E_ARG;
 }

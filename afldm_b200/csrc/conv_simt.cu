@@ -199,36 +199,71 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(const ConvArgs a) {
     }
 }
 
-// Shared with the tensor-core path: y = sum_z ws[z] + bias + row_add + residual.
-__global__ void __launch_bounds__(256)
+// Shared with the tensor-core path: y = sum_z ws[z] + bias + row_add + residual, summed in a fixed
+// order.  One thread owns one output channel of one image and walks its HW rows (consecutive
+// threads = consecutive channels: coalesced), so the per-(image, channel) GroupNorm partial sums
+// (sum, sum of squares) of the finished output fall out for free (gn_partial [B][1][Cout] float2 | NULL).
+constexpr int RED_COLS = 32, RED_ROWL = 8;     // CTA: 32 channels x 8 row lanes, RED_ROWS rows of one image
+
+__global__ void __launch_bounds__(RED_COLS * RED_ROWL)
 splitk_reduce_kernel(const float* __restrict__ ws, int splitk, const float* __restrict__ bias,
                      const float* __restrict__ row_add, int row_add_pitch, const float* residual,
-                     int res_pitch, float* y, int y_pitch, int M, int Cout, int HW) {
+                     int res_pitch, float* y, int y_pitch, int M, int Cout, int HW, float* gn_partial) {
     pdl_trigger();
     pdl_wait();
-    const long long total = (long long)M * Cout;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int m = (int)(i / Cout), n = (int)(i % Cout);
-        float v = 0.f;
-        for (int z = 0; z < splitk; ++z) v += ws[(size_t)z * total + i];
-        if (bias != nullptr) v += bias[n];
-        if (row_add != nullptr) v += row_add[(size_t)(m / HW) * row_add_pitch + n];
-        if (residual != nullptr) v += residual[(size_t)m * res_pitch + n];
-        y[(size_t)m * y_pitch + n] = v;
+    __shared__ float2 red[RED_ROWL][RED_COLS];
+    const int slot = blockIdx.z, slots = gridDim.z;
+    const int col = threadIdx.x % RED_COLS, rl = threadIdx.x / RED_COLS;
+    const int n = blockIdx.x * RED_COLS + col;
+    const int b = blockIdx.y;
+    const bool ok = n < Cout;
+    const size_t total = (size_t)M * Cout;
+    float s = 0.f, q = 0.f;
+    if (ok) {
+        const float add = (bias != nullptr ? bias[n] : 0.f) +
+                          (row_add != nullptr ? row_add[(size_t)b * row_add_pitch + n] : 0.f);
+        const int m_beg = b * HW + slot * SPLITK_REDUCE_ROWS;
+        const int m_end = min(M, min((b + 1) * HW, m_beg + SPLITK_REDUCE_ROWS));
+        for (int m = m_beg + rl; m < m_end; m += RED_ROWL) {
+            const float* p = ws + (size_t)m * Cout + n;
+            float v = 0.f;
+            int z = 0;
+            for (; z + 4 <= splitk; z += 4) {   // 4 loads in flight, summed in z order
+                const float v0 = p[(size_t)z * total], v1 = p[(size_t)(z + 1) * total];
+                const float v2 = p[(size_t)(z + 2) * total], v3 = p[(size_t)(z + 3) * total];
+                v = (((v + v0) + v1) + v2) + v3;
+            }
+            for (; z < splitk; ++z) v += p[(size_t)z * total];
+            v += add;
+            if (residual != nullptr) v += residual[(size_t)m * res_pitch + n];
+            y[(size_t)m * y_pitch + n] = v;
+            s += v;
+            q = fmaf(v, v, q);
+        }
+    }
+    if (gn_partial == nullptr) return;
+    red[rl][col] = make_float2(s, q);
+    __syncthreads();
+    if (rl == 0 && ok) {
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int r = 0; r < RED_ROWL; ++r) {    // fixed order
+            ts += red[r][col].x;
+            tq += red[r][col].y;
+        }
+        reinterpret_cast<float2*>(gn_partial)[((size_t)b * slots + slot) * Cout + n] = make_float2(ts, tq);
     }
 }
 
 }  // namespace
 
 void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const float* row_add,
-                          int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int M, int Cout,
-                          int HW, cudaStream_t st) {
-    const long long total = (long long)M * Cout;
-    const int blocks = (int)std::min<long long>(148 * 4, (total + 255) / 256);
-    launch_k(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, ws, splitk, bias, row_add, row_add_pitch, residual, res_pitch, y,
-                                                 y_pitch,
-                                                 M, Cout, HW);
+                          int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int M,
+                          int Cout, int HW, float* gn_partial, cudaStream_t st) {
+    const int B = ceil_div(M, HW);
+    launch_k(splitk_reduce_kernel, dim3(ceil_div(Cout, RED_COLS), B, splitk_reduce_slots(HW)),
+             dim3(RED_COLS * RED_ROWL), 0, st, ws, splitk, bias, row_add,
+             row_add_pitch, residual, res_pitch, y, y_pitch, M, Cout, HW, gn_partial);
 }
 
 int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* bias,
@@ -253,7 +288,7 @@ int conv_simt_launch(const float* x, int x_pitch, const float* w, const float* b
     int launches = 1;
     if (p.splitk > 1) {
         splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, p.M, Cout,
-                             H * W, st);
+                             H * W, nullptr, st);
         ++launches;
     }
     return launched(launches);

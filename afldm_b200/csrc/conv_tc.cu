@@ -36,7 +36,7 @@ constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = on
 constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
 constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
 constexpr int SMEM_BUDGET = 184 * 1024;          // one CTA per SM (dynamic part; ~19 KB static on top)
-constexpr int SMEM_TWO_PER_SM = 90 * 1024;       // dynamic part that still lets two CTAs share an SM
+constexpr int SMEM_TWO_PER_SM = 85 * 1024;       // dynamic part that still lets two CTAs share an SM
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_PITCH = 36;
 constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
@@ -131,6 +131,8 @@ struct TcArgs {
     int W, H;                       // image size
     int BW, BH;                     // box geometry (BB implied)
     int vec_ok;                     // all epilogue pointers / pitches allow float4 access
+    float* gn_partial;              // [B][gn_slots][Cout] float2 GroupNorm partial sums of the output | NULL
+    int gn_slots;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -143,6 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ uint32_t tmem_base_slot;
     // epilogue transpose staging: per epilogue warp 32 rows x (32 + 4) floats (pitch 36: conflict-free both ways)
     __shared__ __align__(16) float epi_stage[4][32 * EPI_PITCH];
+    __shared__ float2 gn_stage[4][192];             // per epilogue warp: (sum, sumsq) of its 32 rows per column
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
@@ -273,6 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             // ... and write it out 4 rows x 128 contiguous bytes per instruction
             const int n = n0 + c + cq * 4;
+            float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
                 const int rr = pass * 4 + rsub;
@@ -295,6 +299,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                     }
                     *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
+                    gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
+                    gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
+                    gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
                 } else {
                     float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -308,7 +315,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            if (a.gn_partial != nullptr) {
+                // rows live in lanes rsub = 0..3 of the same column quad: fold them, lanes 0..7 keep the totals
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 8);
+                    gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 8);
+                    gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 16);
+                    gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 16);
+                }
+                if (rsub == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) gn_stage[q][c + cq * 4 + j] = make_float2(gs[j], gq[j]);
+                }
+            }
             __syncwarp();
+        }
+        if (a.gn_partial != nullptr) {
+            // combine the four row quarters (fixed order) and publish one partial per (tile, channel)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = threadIdx.x - 64;            // 0..127 over the epilogue warps
+            const int bimg = m0 / a.HW;
+            const int slot = (m0 - bimg * a.HW) / TBM;
+            for (int col = et; col < a.BN; col += 128) {
+                const int n = n0 + col;
+                if (n >= a.Cout) continue;
+                const float2 p0 = gn_stage[0][col], p1 = gn_stage[1][col], p2 = gn_stage[2][col], p3 = gn_stage[3][col];
+                reinterpret_cast<float2*>(a.gn_partial)[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
+                    make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
+            }
         }
     }
 
@@ -413,6 +448,14 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
 
 }  // namespace
 
+int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    if (!p.ok || (Cout & 3) != 0 || p.BN > 192) return 0;
+    if (p.splitk > 1) return splitk_reduce_slots(H * W);  // the split-K reduce emits one slot per 16 rows
+    const int HW = H * W;
+    return (HW % TBM == 0) ? HW / TBM : 0;               // a 128-pixel tile must stay inside one image
+}
+
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
     if (!p.ok) return false;
@@ -422,8 +465,11 @@ bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, si
 
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H,
-                   int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, cudaStream_t st) {
+                   int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
+                   cudaStream_t st) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    const int gn_slots = gn_partial != nullptr ? conv_tc_gn_slots(B, H, W, Cin, Cout, ks) : 0;
+    if (gn_partial != nullptr && gn_slots == 0) return AFLDM_E_SHAPE;
     if (!p.ok || (x_pitch & 3) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return AFLDM_E_NOKERNEL;
@@ -469,6 +515,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.iters_per_split = p.iters_per_split;
     a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
+    a.gn_partial = (p.splitk > 1) ? nullptr : gn_partial;
+    a.gn_slots = gn_slots;
     a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
@@ -477,7 +525,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     int launches = 1;
     if (p.splitk > 1) {
         splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch,
-                             p.M, Cout, H * W, st);
+                             p.M, Cout, H * W, gn_partial, st);
         ++launches;
     }
     return launched(launches);

@@ -80,6 +80,49 @@ gn_stats_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     }
 }
 
+// GroupNorm finalize from partial sums that the producing kernels emitted (conv epilogue / split-K
+// reduce): partial [B][slots][Cx] float2 per source; channels [0, Ca) come from source a, the rest from
+// source b (the two halves of a skip-connection concat).  One warp per (b, group), fp64 combine.
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float2* __restrict__ pa, int slots_a, int Ca, const float2* __restrict__ pb, int slots_b,
+                   int Cb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ scale, float* __restrict__ shift, int B, int HW, int groups, float eps) {
+    pdl_trigger();
+    pdl_wait();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * groups) return;
+    const int C = Ca + Cb;
+    const int b = warp / groups, g = warp % groups;
+    const int cpg = C / groups;
+    double s = 0.0, q = 0.0;
+    // lanes stride over the group's (slot, channel) partials: channel fastest = contiguous float2 loads
+    const int slots_max = max(slots_a, slots_b);
+    for (int it = lane; it < slots_max * cpg; it += 32) {
+        const int sl = it / cpg, c = g * cpg + (it - sl * cpg);
+        float2 v = make_float2(0.f, 0.f);
+        if (c < Ca) {
+            if (sl < slots_a) v = pa[((size_t)b * slots_a + sl) * Ca + c];
+        } else {
+            if (sl < slots_b) v = pb[((size_t)b * slots_b + sl) * Cb + (c - Ca)];
+        }
+        s += (double)v.x;
+        q += (double)v.y;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const double n = (double)HW * (double)cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps)), fmean = (float)mean;
+    for (int cc = lane; cc < cpg; cc += 32) {
+        const int c = g * cpg + cc;
+        const float sc = (gamma != nullptr ? gamma[c] : 1.f) * rstd;
+        scale[(size_t)b * C + c] = sc;
+        shift[(size_t)b * C + c] = fmaf(-fmean, sc, beta != nullptr ? beta[c] : 0.f);
+    }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, int C4,
@@ -122,6 +165,21 @@ extern "C" int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, 
     if (C % groups != 0) return AFLDM_E_SHAPE;
     if ((long long)HW * (C / groups) > 0x7fffffffLL) return AFLDM_E_SHAPE;
     launch_k(gn_stats_kernel, dim3(B * groups), dim3(256), 0, as_stream(stream), x, gamma, beta, scale, shift, HW, C, groups, eps);
+    return launched();
+}
+
+extern "C" int afldm_groupnorm_finalize_f32(const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                            int slots_b, int Cb, int B, int HW, int groups, float eps,
+                                            const float* gamma, const float* beta, float* scale, float* shift,
+                                            afldm_stream_t stream) {
+    if (partial_a == nullptr || scale == nullptr || shift == nullptr) return AFLDM_E_ARG;
+    if (B <= 0 || HW <= 0 || Ca <= 0 || slots_a <= 0 || groups <= 0 || Cb < 0) return AFLDM_E_ARG;
+    if (Cb > 0 && (partial_b == nullptr || slots_b <= 0)) return AFLDM_E_ARG;
+    if ((Ca + Cb) % groups != 0) return AFLDM_E_SHAPE;
+    const int warps = B * groups;
+    launch_k(gn_finalize_kernel, dim3(ceil_div(warps, 4)), dim3(128), 0, as_stream(stream),
+             reinterpret_cast<const float2*>(partial_a), slots_a, Ca, reinterpret_cast<const float2*>(partial_b),
+             slots_b, Cb, gamma, beta, scale, shift, B, HW, groups, eps);
     return launched();
 }
 

@@ -55,15 +55,15 @@ class ResnetBlock2D(nn.Module):
             temb_proj = ops.linear_rows(temb.contiguous(), self.time_emb_proj.weight, self.time_emb_proj.bias,
                                         act_in="silu")
         w1, b1, k1 = conv_params(self.conv1)
-        h = ops.conv2d(norm_act(x, self.norm1, self.nonlinearity), w1, b1, k1, row_add=temb_proj)
+        h = ops.conv2d(norm_act(x, self.norm1, self.nonlinearity), w1, b1, k1, row_add=temb_proj, gn_stats=True)
         a = norm_act(h, self.norm2, self.nonlinearity)
         w2, b2, k2 = conv_params(self.conv2)
         if self.conv_shortcut is not None:
             ws, bs, ks = conv_params(self.conv_shortcut)
             sc = ops.conv2d(x, ws, bs, ks)
-            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc)
+            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc, gn_stats=True)
         else:
-            out = ops.conv2d(a, w2, b2, k2, residual=x)
+            out = ops.conv2d(a, w2, b2, k2, residual=x, gn_stats=True)
         return ops.nchw_view(out)
 
 
@@ -106,7 +106,8 @@ class AttnProcessor2_0:
         else:
             o = ops.attention_gemm(q, k, v, attn.heads)
         wo, bo, _ = conv_params(attn.to_out[0])
-        out = ops.conv2d(o.view(b, h, w, c), wo, bo, 1, residual=x if attn.residual_connection else None)
+        out = ops.conv2d(o.view(b, h, w, c), wo, bo, 1, residual=x if attn.residual_connection else None,
+                         gn_stats=True)
         if attn.rescale_output_factor != 1.0:
             raise NotImplementedError("rescale_output_factor != 1")
         return ops.nchw_view(out)

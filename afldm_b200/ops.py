@@ -93,7 +93,7 @@ def nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical [B,C,H,W] -> physical [B,H,W,C] contiguous (zero-copy for channels_last input)."""
     v = x.permute(0, 2, 3, 1)
     if v.is_contiguous():
-        return v
+        return _carry_gn(x, v)
     x = _chk(x.contiguous(), "x")
     b, c, h, w = x.shape
     y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
@@ -105,7 +105,16 @@ def nhwc(x: torch.Tensor) -> torch.Tensor:
 
 def nchw_view(y: torch.Tensor) -> torch.Tensor:
     """Physical [B,H,W,C] -> logical [B,C,H,W] (channels_last strides, zero-copy)."""
-    return y.permute(0, 3, 1, 2)
+    return _carry_gn(y, y.permute(0, 3, 1, 2))
+
+
+def _carry_gn(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """Views of one buffer share the GroupNorm partial sums its producing kernel emitted."""
+    for name in ("_afldm_gn", "_afldm_gn2"):
+        st = getattr(src, name, None)
+        if st is not None:
+            setattr(dst, name, st)
+    return dst
 
 
 def to_nchw_contiguous(y: torch.Tensor) -> torch.Tensor:
@@ -176,6 +185,17 @@ def groupnorm_affine(x: torch.Tensor, groups: int, eps: float, gamma: Optional[t
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
     L = _lib.lib()
+    one, two = getattr(x, "_afldm_gn", None), getattr(x, "_afldm_gn2", None)
+    if one is not None or two is not None:
+        # the kernel(s) that produced x already emitted its partial sums: no pass over x
+        (pa, sa, ca), (pb, sb, cb) = (one, (None, 0, 0)) if one is not None else two
+        if ca + cb == c:
+            ss = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
+            _run("groupnorm_finalize", dict(B=b, HW=hw, C=c, elems=b * c),
+                 lambda: L.afldm_groupnorm_finalize_f32(pa.data_ptr(), sa, ca, _ptr(pb), sb, cb, b, hw, groups,
+                                                        float(eps), _ptr(gamma), _ptr(beta), ss[0].data_ptr(),
+                                                        ss[1].data_ptr(), _stream()), (pa, pb, gamma, beta, ss))
+            return ss[0], ss[1]
     need = L.afldm_groupnorm_scratch_floats(b, hw, c)
     part = scratch(x.device, need) if need else None
     ss = torch.empty((2, b, c), dtype=torch.float32, device=x.device)
@@ -211,9 +231,10 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
            row_add: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           out: Optional[torch.Tensor] = None, algo: Optional[str] = None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, algo: Optional[str] = None, gn_stats: bool = False) -> torch.Tensor:
     """Stride-1 'same' convolution (k = 1 or 3) of NHWC x with the fused epilogue
-    ``+ bias + row_add[b] + residual``.  ``x``, ``residual`` and ``out`` may be channel slices of
+    ``+ bias + row_add[b] + residual``.  ``gn_stats``: also emit the GroupNorm partial sums of the output
+    (tensor-core path), attached to the returned tensor for ``groupnorm_affine`` to pick up.  ``x``, ``residual`` and ``out`` may be channel slices of
     wider NHWC buffers (last-dim stride 1, pixel pitch = stride(-2))."""
     L = _lib.lib()
     b, h, w_, cin = x.shape
@@ -234,19 +255,27 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     meta = dict(B=b, H=h, W=w_, Cin=cin, Cout=cout, k=ksize, flops=2.0 * b * h * w_ * cout * ksize * ksize * cin)
     keep = (x, w_packed, bias, row_add, residual, out)
 
-    def call(a: int, ws, need: int):
+    for stale in ("_afldm_gn", "_afldm_gn2"):
+        if hasattr(out, stale):
+            delattr(out, stale)
+
+    def call(a: int, ws, need: int, gn=None):
         return L.afldm_conv2d_f32(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), _ptr(row_add), ra_pitch,
                                   _ptr(residual), res_pitch, out.data_ptr(), y_pitch, b, h, w_, cin, cout, ksize,
-                                  a, _ptr(ws), need, _stream())
+                                  a, _ptr(ws), need, _ptr(gn), _stream())
 
     if CONV_ALGO[name] == 1:
         need = L.afldm_conv2d_workspace_floats(b, h, w_, cin, cout, ksize, 1)
         ws = scratch(x.device, need) if need else None
-        code = call(1, ws, need)
+        slots = L.afldm_conv2d_gn_slots(b, h, w_, cin, cout, ksize, 1) if gn_stats else 0
+        gn = torch.empty((b, slots, cout, 2), dtype=torch.float32, device=x.device) if slots else None
+        code = call(1, ws, need, gn)
         if code != -3:      # AFLDM_E_NOKERNEL: shape outside the tensor-core family -> exact SIMT kernel
             _lib.check(code, "conv2d[tf32]")
             if _recorder is not None:
-                _recorder.append(("conv2d_tf32", meta, lambda: call(1, ws, need), keep + (ws,)))
+                _recorder.append(("conv2d_tf32", meta, lambda: call(1, ws, need, gn), keep + (ws, gn)))
+            if gn is not None:
+                out._afldm_gn = (gn, slots, cout)
             return out
     need0 = L.afldm_conv2d_workspace_floats(b, h, w_, cin, cout, ksize, 0)
     ws0 = scratch(x.device, need0) if need0 else None
@@ -359,6 +388,9 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     _run("concat_channels", dict(elems=y.numel()),
          lambda: L.afldm_concat_channels_f32(a.data_ptr(), ca, b.data_ptr(), cb, y.data_ptr(), pixels, _stream()),
          (a, b, y))
+    ga, gb = getattr(a, "_afldm_gn", None), getattr(b, "_afldm_gn", None)
+    if ga is not None and gb is not None:
+        y._afldm_gn2 = (ga, gb)         # statistics of a concat = the statistics of its two halves
     return y
 
 

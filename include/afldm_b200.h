@@ -95,6 +95,15 @@ AFLDM_API int afldm_groupnorm_affine_f32(const float* x, int B, int HW, int C, i
                                const float* gamma, const float* beta,
                                float* scale, float* shift, float* partial, afldm_stream_t stream);
 
+/* The same scale / shift from partial sums emitted by the producer of x instead of a pass over x:
+ * afldm_conv2d_f32 (tensor-core path) writes gn_partial [B][slots][C] float2 (sum, sum of squares over the
+ * slot's pixels).  Channels [0,Ca) are taken from partial_a, [Ca,Ca+Cb) from partial_b - the two inputs
+ * of a skip-connection torch.cat - pass Cb = 0 / NULL for a single source. */
+AFLDM_API int afldm_groupnorm_finalize_f32(const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                           int slots_b, int Cb, int B, int HW, int groups, float eps,
+                                           const float* gamma, const float* beta, float* scale, float* shift,
+                                           afldm_stream_t stream);
+
 /* y = act(x*scale[b,c] + shift[b,c]); x, y NHWC [B,HW,C] (plain nn.SiLU after a norm: UNet tail
  * conv_norm_out/conv_act, VAE blocks with up_filtered_act=false; act = identity gives the
  * normalised input of an attention block). scale/shift may be NULL. x may alias y. */
@@ -115,12 +124,17 @@ AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int 
  *       AFLDM_CONV_TCGEN05_TF32 = tcgen05 tensor cores, TF32 operands, fp32 accumulate in TMEM
  *       (same numeric class as the reference's default cuDNN path; falls back to
  *       AFLDM_E_NOKERNEL when the shape does not fit: Cin % 32, Cout % 16, W power of two).
- * workspace: split-K partial sums, afldm_conv2d_workspace_floats(...) floats (may be 0). */
+ * workspace: split-K partial sums, afldm_conv2d_workspace_floats(...) floats (may be 0).
+ * gn_partial: NULL, or [B][slots][Cout] float2 that receives the GroupNorm partial sums of y (the next
+ *       layer's norm then needs no pass over y); slots = afldm_conv2d_gn_slots(...), 0 = not available
+ *       for this shape / algo (then gn_partial must be NULL). */
+AFLDM_API int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
                      const float* row_add, int row_add_pitch, const float* residual, int res_pitch,
                      float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
-                     int algo, float* workspace, size_t workspace_floats, afldm_stream_t stream);
+                     int algo, float* workspace, size_t workspace_floats, float* gn_partial,
+                     afldm_stream_t stream);
 
 /* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
  * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */

@@ -50,7 +50,7 @@ def test_argument_checks_do_not_need_a_gpu(built):
     assert lib.afldm_filtered_act_f32(None, None, 1, 8, 8, 32, 1, None, None, None, 0, None) == -2
     assert lib.afldm_resample_workspace_floats(0, 2, 32, 32, 64) == 0
     assert lib.afldm_resample_workspace_floats(0, 2, 64, 64, 64) == 2 * 2 * 64 * 128 * 64
-    assert lib.afldm_conv2d_f32(None, 4, None, None, None, 0, None, 0, None, 4, 1, 2, 2, 4, 4, 3, 0, None, 0, None) == -2
+    assert lib.afldm_conv2d_f32(None, 4, None, None, None, 0, None, 0, None, 4, 1, 2, 2, 4, 4, 3, 0, None, 0, None, None) == -2
     assert lib.afldm_groupnorm_scratch_floats(16, 1024, 192) == 0
     assert lib.afldm_conv2d_workspace_floats(16, 32, 32, 192, 192, 3, 0) == 0      # 128 x 3 tiles: no split-K
     assert lib.afldm_conv2d_workspace_floats(16, 2, 2, 1536, 768, 3, 0) > 0        # 2x2 level: split-K

@@ -93,3 +93,34 @@ def test_tcgen05_split_k_is_deterministic():
     a, _ = run_tc(x, wp, None, 3)
     b, _ = run_tc(x, wp, None, 3)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("b,h,cin,cout,k", [(2, 32, 64, 192, 3), (3, 16, 128, 96, 1), (4, 8, 384, 384, 3), (16, 2, 768, 768, 3)])
+def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
+    """GroupNorm scale/shift finalised from the partial sums the conv epilogue (or the split-K reduce)
+    emits == the standalone statistics pass over the conv output."""
+    x = nhwc(randn(b, cin, h, h, seed=1))
+    wp = ops.pack_conv_weight(randn(cout, cin, k, k, seed=2) * (1.0 / (cin * k * k) ** 0.5))
+    bias, res = randn(cout, seed=3), nhwc(randn(b, cout, h, h, seed=4))
+    gamma, beta = randn(cout, seed=5) * 0.2 + 1, randn(cout, seed=6) * 0.2
+    y = ops.conv2d(x, wp, bias, k, residual=res, algo="tf32", gn_stats=True)
+    assert hasattr(y, "_afldm_gn")
+    rec = []
+    ops.record_to(rec)
+    s1, t1 = ops.groupnorm_affine(y, 32, 1e-5, gamma, beta)
+    ops.record_to(None)
+    assert [r[0] for r in rec] == ["groupnorm_finalize"]
+    s0, t0 = ops.groupnorm_affine(y.clone(), 32, 1e-5, gamma, beta)          # clone drops the attribute
+    torch.testing.assert_close(s1, s0, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(t1, t0, rtol=0, atol=2e-5)
+    # through the zero-copy layout views and a channel concat of two producers
+    v = ops.nhwc(ops.nchw_view(y))
+    assert hasattr(v, "_afldm_gn")
+    y2 = ops.conv2d(x, wp, None, k, algo="tf32", gn_stats=True)
+    cat = ops.concat_channels(y, y2)
+    assert hasattr(cat, "_afldm_gn2")
+    g2, b2 = torch.cat([gamma, gamma]), torch.cat([beta, beta])
+    sc, tc = ops.groupnorm_affine(cat, 32, 1e-5, g2, b2)
+    sr, tr = ops.groupnorm_affine(cat.clone(), 32, 1e-5, g2, b2)
+    torch.testing.assert_close(sc, sr, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(tc, tr, rtol=0, atol=2e-5)
