@@ -172,14 +172,40 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
     constexpr int KT = 64;            // keys per tile
     constexpr int P = D + 4;          // smem row pitch (words)
     constexpr int DK = D / 8;         // k-steps of Q.K^T == n-tiles of P.V
-    __shared__ __align__(16) float Ks[KT * P];
-    __shared__ __align__(16) float Vs[KT * P];
+    constexpr int D4 = D / 4;
+    // double-buffered K / V tiles: tile i+1 streams in with cp.async while tile i is consumed
+    extern __shared__ __align__(16) float att_smem[];          // [K0 | K1 | V0 | V1], each KT * P floats
+    auto Kbuf = [&](int i) { return att_smem + i * (KT * P); };
+    auto Vbuf = [&](int i) { return att_smem + (2 + i) * (KT * P); };
     const int b = blockIdx.z, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int bkv = b / Bkv_rep;
     const int row0 = blockIdx.x * 64 + warp * 16 + g;      // this lane's rows: row0 and row0 + 8
     const int row1 = row0 + 8;
+
+    const float* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    const float* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    auto load_tile = [&](int buf, int k0) {
+        const int nk = min(KT, Nk - k0);
+        for (int idx = threadIdx.x; idx < KT * D4; idx += blockDim.x) {
+            const int key = idx / D4, c4 = idx - key * D4;
+            float* kd = Kbuf(buf) + key * P + 4 * c4;
+            float* vd = Vbuf(buf) + key * P + 4 * c4;
+            if (key < nk) {
+                const uint32_t ks_ = (uint32_t)__cvta_generic_to_shared(kd), vs_ = (uint32_t)__cvta_generic_to_shared(vd);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_),
+                             "l"(kbase + (size_t)(k0 + key) * kv_pitch + 4 * c4) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_),
+                             "l"(vbase + (size_t)(k0 + key) * kv_pitch + 4 * c4) : "memory");
+            } else {
+                *reinterpret_cast<float4*>(kd) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(vd) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_tile(0, 0);
 
     // Q fragments (scaled into the exp2 domain, rounded to TF32 once)
     uint32_t qa[DK][4];
@@ -201,31 +227,25 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
         for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-    const float* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
-    const float* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
-    constexpr int D4 = D / 4;
-
-    for (int k0 = 0; k0 < Nk; k0 += KT) {
+    int buf = 0;
+    for (int k0 = 0; k0 < Nk; k0 += KT, buf ^= 1) {
         const int nk = min(KT, Nk - k0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < KT * D4; idx += blockDim.x) {
-            const int key = idx / D4, c4 = idx - key * D4;
-            float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
-            if (key < nk) {
-                kv4 = *reinterpret_cast<const float4*>(kbase + (size_t)(k0 + key) * kv_pitch + 4 * c4);
-                vv4 = *reinterpret_cast<const float4*>(vbase + (size_t)(k0 + key) * kv_pitch + 4 * c4);
-            }
-            *reinterpret_cast<float4*>(&Ks[key * P + 4 * c4]) = kv4;
-            *reinterpret_cast<float4*>(&Vs[key * P + 4 * c4]) = vv4;
+        if (k0 + KT < Nk) {
+            load_tile(buf ^ 1, k0 + KT);                       // prefetch the next tile
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const float* Kt = Kbuf(buf);
+        const float* Vt = Vbuf(buf);
 
         // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            const float* kr = &Ks[(nt * 8 + g) * P + t];
+            const float* kr = &Kt[(nt * 8 + g) * P + t];
 #pragma unroll
             for (int ks = 0; ks < DK; ++ks)
                 mma_tf32(s[nt], qa[ks], __float_as_uint(kr[8 * ks]), __float_as_uint(kr[8 * ks + 4]));
@@ -262,12 +282,13 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
             l1 += p10 + p11;
             // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
             const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
-            const float* vr0 = &Vs[(nt * 8 + 2 * t) * P + g];
+            const float* vr0 = &Vt[(nt * 8 + 2 * t) * P + g];
             const float* vr1 = vr0 + P;
 #pragma unroll
             for (int dn = 0; dn < DK; ++dn)
                 mma_tf32(oacc[dn], pa, __float_as_uint(vr0[8 * dn]), __float_as_uint(vr1[8 * dn]));
         }
+        __syncthreads();                                       // everyone is done with `buf` before it is refilled
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -292,7 +313,14 @@ template <int D>
 int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
                int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
     const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
-    launch_k(attention_mma_kernel<D>, dim3(ceil_div(Nq, 64), heads, B), dim3(128), 0, st, 
+    constexpr int smem = 4 * 64 * (D + 4) * 4;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+    launch_k(attention_mma_kernel<D>, dim3(ceil_div(Nq, 64), heads, B), dim3(128), smem, st, 
         q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
     return launched();
 }

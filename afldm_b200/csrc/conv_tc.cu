@@ -35,8 +35,11 @@ constexpr int TBM = 128;           // output pixels per tile (UMMA M)
 constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
 constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
-constexpr int SMEM_BUDGET = 184 * 1024;          // one CTA per SM (dynamic part; ~19 KB static on top)
-constexpr int SMEM_TWO_PER_SM = 85 * 1024;       // dynamic part that still lets two CTAs share an SM
+// All shared memory is dynamic: [stage ring | mbarriers + TMEM slot (SMEM_TAIL bytes)].  The epilogue's
+// staging tiles alias the (by then idle) stage ring, so the whole 227 KB goes to operands in flight.
+constexpr int SMEM_TAIL = 256;
+constexpr int SMEM_BUDGET = 224 * 1024;                          // stage ring, one CTA per SM
+constexpr int SMEM_TWO_PER_SM = (232448 / 2) - 1024 - SMEM_TAIL; // stage ring that lets two CTAs share an SM
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_PITCH = 36;
 constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
@@ -68,6 +71,64 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// Multicast variant: the box is written at the same shared-memory offset of every CTA in cta_mask and
+// completes bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               int c2, int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256), each CTA stages its own 128 rows
+// of A and HALF of the B tile; TMA completions and MMA commits are routed to the leader CTA's barriers.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                             int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -133,25 +194,35 @@ struct TcArgs {
     int vec_ok;                     // all epilogue pointers / pitches allow float4 access
     float* gn_partial;              // [B][gn_slots][Cout] float2 GroupNorm partial sums of the output | NULL
     int gn_slots;
+    int cluster;                    // CTAs along N that share (multicast) one A tile: 1, 2 or 4
+    int slice_dim;                  // which box dim the A tile is sliced along for the multicast (1 = W, 2 = H, 3 = B)
+    int slice_step;                 // coordinate step between consecutive slices
 };
 
+// TWO = false: one CTA per 128 x BN tile (cta_group::1).
+// TWO = true : a cluster of two CTAs (consecutive blockIdx.x = consecutive M tiles) computes 256 x BN with
+//              tcgen05.mma.cta_group::2 issued by the even CTA; each CTA stages 128 rows of A and BN/2 rows of B,
+//              i.e. 16 KB + BN*64 B per stage instead of 16 KB + BN*128 B - the SM's operand ingest (the measured
+//              bound of the main loop) buys up to 2x the FLOPs.
+template <bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t accum_bar;
-    __shared__ uint32_t tmem_base_slot;
-    // epilogue transpose staging: per epilogue warp 32 rows x (32 + 4) floats (pitch 36: conflict-free both ways)
-    __shared__ __align__(16) float epi_stage[4][32 * EPI_PITCH];
-    __shared__ float2 gn_stage[4][192];             // per epilogue warp: (sum, sumsq) of its 32 rows per column
-
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static smem: the ring starts 1024-aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // dynamic smem base rounded up to 1024 B (swizzle-128B atoms)
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int b_stage_bytes = a.BN * TBK * 4;
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if ((smem_base & 1023u) != 0u) __trap();                 // swizzle-128B atoms need 1024 B alignment
+    const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * TBK * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)a.stages * stage_bytes);
+    uint64_t* const empty_bar = full_bar + MAX_STAGES;
+    uint64_t* const accum_bar_p = empty_bar + MAX_STAGES;
+    uint32_t* const tmem_slot_p = reinterpret_cast<uint32_t*>(accum_bar_p + 1);
+    // epilogue staging (aliases the stage ring, idle once the accumulator is complete):
+    //   per epilogue warp 32 rows x (32 + 4) floats (pitch 36: conflict-free both ways), then the
+    //   per-warp GroupNorm (sum, sumsq) of 32 rows per column
+    float (*epi_stage)[32 * EPI_PITCH] = reinterpret_cast<float (*)[32 * EPI_PITCH]>(smem_raw);
+    float2 (*gn_stage)[192] = reinterpret_cast<float2 (*)[192]>(smem_raw + 4 * 32 * EPI_PITCH * 4);
 
     const int total_iters = a.taps * a.cin_chunks;
     const int it_beg = blockIdx.z * a.iters_per_split;
@@ -161,17 +232,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), (uint32_t)a.cluster);   // one MMA commit per CTA of the cluster
         }
-        mbar_init(smem_u32(&accum_bar), 1);
+        mbar_init(smem_u32(accum_bar_p), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_slot)), "r"((uint32_t)a.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (TWO) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_slot_p)), "r"((uint32_t)a.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_slot_p)), "r"((uint32_t)a.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -179,8 +257,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (TWO || a.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_base = *tmem_slot_p;
+    const uint32_t crank = (TWO || a.cluster > 1) ? cluster_rank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << a.cluster) - 1u);
     // Everything above touched only this CTA's shared / tensor memory: it may overlap the tail of the
     // previous kernel on the stream.  From here on global memory is read.
     pdl_trigger();
@@ -188,6 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int m0 = blockIdx.x * TBM;
     const int n0 = blockIdx.y * a.BN;
+    const bool mma_leader = !TWO || crank == 0u;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -220,18 +302,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int dh = tap / a.ks - pad, dw = tap % a.ks - pad;
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 const uint32_t sa = smem_base + s * stage_bytes;
+                if constexpr (TWO) {
+                    // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+                    if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
+                    tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                    tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
+                    continue;
+                }
                 mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                if (a.cluster == 1) {
+                    tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                } else {
+                    // this CTA fetches slice `crank` of the shared A tile and multicasts it to the whole cluster
+                    const int off = (int)crank * a.slice_step;
+                    const int cw = w0 + dw + (a.slice_dim == 1 ? off : 0);
+                    const int chh = h0 + dh + (a.slice_dim == 2 ? off : 0);
+                    const int cb = b0 + (a.slice_dim == 3 ? off : 0);
+                    tma_load_4d_mc(sa + crank * (A_STAGE_BYTES / a.cluster), &map_a, fb, c0, cw, chh, cb, cmask);
+                }
                 tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && n_iters > 0) {
+        if (lane == 0 && n_iters > 0 && mma_leader) {
             // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both,
-            // N >> 3 at bit 17, M >> 4 at bit 24
+            // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
-                                   ((uint32_t)(TBM >> 4) << 24);
+                                   ((uint32_t)((TWO ? 2 * TBM : TBM) >> 4) << 24);
             for (int i = 0; i < n_iters; ++i) {
                 const int s = i % a.stages;
                 const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
@@ -242,18 +340,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < TBK / UMMA_K; ++k) {
                     // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                    umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                    if constexpr (TWO) umma2_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                    else umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(smem_u32(&empty_bar[s]));   // frees the stage when these MMAs retire
+                // frees the stage (in every CTA that writes into it) when these MMAs retire
+                if constexpr (TWO) umma2_commit_mc(smem_u32(&empty_bar[s]), 3);
+                else if (a.cluster == 1) umma_commit(smem_u32(&empty_bar[s]));
+                else umma_commit_mc(smem_u32(&empty_bar[s]), cmask);
             }
-            umma_commit(smem_u32(&accum_bar));          // accumulator complete
+            // accumulator complete (in both CTAs of a pair)
+            if constexpr (TWO) umma2_commit_mc(smem_u32(accum_bar_p), 3);
+            else umma_commit(smem_u32(accum_bar_p));
         }
     } else {
         // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
         const int q = warp & 3;
         const bool split = gridDim.z > 1;
         if (n_iters > 0) {
-            mbar_wait(smem_u32(&accum_bar), 0);
+            mbar_wait(smem_u32(accum_bar_p), 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         float* stg = epi_stage[q];
@@ -349,9 +453,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (TWO || a.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
-                     : "memory");
+        if constexpr (TWO)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                         : "memory");
     }
 }
 
@@ -378,6 +487,8 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 struct TcPlan {
     bool ok;
     int M, mtiles, ntiles, BN, stages, tmem_cols, total_iters, splitk, iters_per_split, BW, BH, BB;
+    int cluster, slice_dim, slice_step, slice_box[3];   // A-tile multicast across N-tile CTAs
+    int two;                                            // CTA-pair (cta_group::2) mode
     size_t smem_bytes;
 };
 
@@ -431,17 +542,63 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     if (Cout % 4 != 0) s = 1;            // split-K partials are written as float4
     p.iters_per_split = ceil_div(p.total_iters, s);
     p.splitk = ceil_div(p.total_iters, p.iters_per_split);
-    const int stage_bytes = A_STAGE_BYTES + p.BN * TBK * 4;
+    // CTA-pair mode (tcgen05.mma.cta_group::2): two consecutive M tiles share every B tile, each CTA stages
+    // only half of it.  For the un-split layers with an even number of M tiles; wide tiles, since the point
+    // is FLOPs per staged byte.
+    static const int allow_two = getenv("AFLDM_TC_TWO") ? atoi(getenv("AFLDM_TC_TWO")) : 1;
+    static const int force_bn2 = getenv("AFLDM_TC2_BN") ? atoi(getenv("AFLDM_TC2_BN")) : 0;
+    p.two = 0;
+    if (allow_two && p.splitk == 1 && p.mtiles % 2 == 0 && p.mtiles >= 32 && Cout >= 64 && Cout % 16 == 0) {
+        // Sweep on B200 (profiles/r01_conv_notes.md): the pair wins on the K-heavy 3x3 layers (up to 1.4x) and
+        // loses on K-light 1x1 layers, and the best width is the one whose grid just fits one wave at two
+        // CTAs per SM (<= 296 CTAs); 1x1 layers only qualify with a wide (>= 128) tile.
+        int bn2 = 0, best_ctas = 0;
+        const int c2[] = {192, 128, 96, 64};
+        for (int bn : c2) {
+            if (Cout % bn != 0) continue;
+            const int ctas = p.mtiles * (Cout / bn);
+            if (ctas <= 296 && ctas > best_ctas) { best_ctas = ctas; bn2 = bn; }
+        }
+        if (bn2 == 0 && ks == 3) {
+            for (int bn : c2)
+                if (Cout % bn == 0) { bn2 = bn; break; }              // very large layer: widest tile
+        }
+        if (ks != 3 && bn2 < 128) bn2 = 0;
+        if (force_bn2 > 0) bn2 = (Cout % force_bn2 == 0 && force_bn2 % 16 == 0 && force_bn2 <= 256) ? force_bn2 : 0;
+        if (bn2 > 0) {
+            p.two = 1;
+            p.BN = bn2;
+            p.ntiles = Cout / bn2;
+        }
+    }
+    const int stage_bytes = A_STAGE_BYTES + (p.two ? p.BN / 2 : p.BN) * TBK * 4;
+    const int tiles2 = p.mtiles * p.ntiles;
     // More CTAs than SMs and a small stage: size the ring so that two CTAs share an SM and one CTA's
     // prologue / epilogue hides behind the other's main loop.
-    const bool two_per_sm = tiles * p.splitk > 148 && 3 * stage_bytes <= SMEM_TWO_PER_SM;
+    const bool two_per_sm = tiles2 * p.splitk > 148 && 3 * stage_bytes <= SMEM_TWO_PER_SM;
     const int budget = two_per_sm ? SMEM_TWO_PER_SM : SMEM_BUDGET;
     p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
     if (force_stages > 0) p.stages = std::min(force_stages, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
     p.stages = std::min(p.stages, std::max(2, p.iters_per_split));
-    p.smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+    p.smem_bytes = (size_t)p.stages * stage_bytes + SMEM_TAIL;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+    // A-tile multicast (opt-in, AFLDM_TC_CLUSTER=2|4): CTAs of the same M tile (consecutive blockIdx.y) form a
+    // cluster; each fetches 1/CL of the 128-pixel A box and multicasts it, cutting the L2 reads of A by CL.
+    // Measured on B200 (profiles/r01_conv_notes.md): no gain - the main loop is bound by bytes in flight per SM
+    // (shared-memory capacity x L2 latency), not by L2 bandwidth, and the cluster couples the CTAs' pipelines.
+    static const int force_cluster = getenv("AFLDM_TC_CLUSTER") ? atoi(getenv("AFLDM_TC_CLUSTER")) : -1;
+    int cl = 1;
+    if (force_cluster >= 1 && p.splitk == 1 && !p.two) cl = (p.ntiles % force_cluster == 0 && (force_cluster == 1 || force_cluster == 2 || force_cluster == 4)) ? force_cluster : 1;
+    p.slice_box[0] = p.BW; p.slice_box[1] = p.BH; p.slice_box[2] = p.BB;
+    p.slice_dim = 0; p.slice_step = 0;
+    while (cl > 1) {
+        if (p.BB > 1 && p.BB % cl == 0) { p.slice_dim = 3; p.slice_step = p.BB / cl; p.slice_box[2] = p.BB / cl; break; }
+        if (p.BB == 1 && p.BH > 1 && p.BH % cl == 0) { p.slice_dim = 2; p.slice_step = p.BH / cl; p.slice_box[1] = p.BH / cl; break; }
+        if (p.BB == 1 && p.BH == 1 && p.BW % cl == 0) { p.slice_dim = 1; p.slice_step = p.BW / cl; p.slice_box[0] = p.BW / cl; break; }
+        cl >>= 1;
+    }
+    p.cluster = cl;
     p.ok = true;
     return p;
 }
@@ -481,7 +638,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * W,
                                        (cuuint64_t)x_pitch * 4 * W * H};
-        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BB};
+        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.slice_box[0], (cuuint32_t)p.slice_box[1],
+                                   (cuuint32_t)p.slice_box[2]};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -492,7 +650,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         const cuuint64_t K = (cuuint64_t)ks * ks * Cin;
         const cuuint64_t dims[2] = {K, (cuuint64_t)Cout};
         const cuuint64_t strides[1] = {K * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)p.BN};
+        const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)(p.two ? p.BN / 2 : p.BN)};
         const cuuint32_t estr[2] = {1, 1};
         if (enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -502,8 +660,11 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
 
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM_BUDGET + 8 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM_BUDGET + SMEM_TAIL);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_BUDGET + SMEM_TAIL);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -520,8 +681,39 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
+    a.cluster = p.cluster; a.slice_dim = p.slice_dim; a.slice_step = p.slice_step;
     dim3 grid(p.mtiles, p.ntiles, p.splitk);
-    launch_k(conv_tc_kernel, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
+    if (p.two) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = p.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, map_a, map_b, a);
+    } else if (p.cluster == 1) {
+        launch_k(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = p.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = (unsigned)p.cluster;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, map_a, map_b, a);
+    }
     int launches = 1;
     if (p.splitk > 1) {
         splitk_reduce_launch(workspace, p.splitk, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch,

@@ -31,7 +31,7 @@ enum { MODE_FACT = 0, MODE_UP2 = 1, MODE_DOWN2 = 2 };
 // o[i] = sum_j d[(i - j) mod N] x[j]
 template <int N>
 __device__ __forceinline__ void up_odd(const float (&x)[N], float (&o)[N]) {
-    constexpr int IB = N >= 4 ? 4 : N;  // independent accumulators for ILP
+    constexpr int IB = N >= 8 ? 8 : N;  // independent accumulators for ILP
 #pragma unroll
     for (int i0 = 0; i0 < N; i0 += IB) {
         float acc[IB];
@@ -50,7 +50,7 @@ __device__ __forceinline__ void up_odd(const float (&x)[N], float (&o)[N]) {
 // y[i] = sum_m g[(2i - m) mod 2N] a[m]
 template <int N>
 __device__ __forceinline__ void down_line(const float (&a)[2 * N], float (&y)[N]) {
-    constexpr int IB = N >= 4 ? 4 : N;
+    constexpr int IB = N >= 8 ? 8 : N;
 #pragma unroll
     for (int i0 = 0; i0 < N; i0 += IB) {
         float acc[IB];
