@@ -52,7 +52,11 @@ inline cudaStream_t as_stream(afldm_stream_t s) { return reinterpret_cast<cudaSt
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.0f + expf(-z)); }
+// SiLU.  exp(-z) as ex2.approx(-z * log2 e) (rel. error ~1e-7 |z| + 2 ulp) and an approximate reciprocal
+// (1 ulp): ~6 instructions instead of ~22 for expf + IEEE division, which matters because the filtered
+// activation applies it 64 times per thread inside an instruction-cache-bound unrolled kernel.  Measured
+// parity vs the reference's exact SiLU stays within the 1e-5 op tolerance (tests/test_gpu_ops.py).
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z) {
