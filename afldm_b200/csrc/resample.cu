@@ -67,6 +67,56 @@ __device__ __forceinline__ void down_line(const float (&a)[2 * N], float (&y)[N]
     }
 }
 
+// Per-(b, c) affine applied on load (GroupNorm folded into the resampler).  Either precomputed scale/shift
+// vectors, or the GroupNorm partial sums that the producer of x emitted (conv epilogue): then every CTA
+// finalises mean / rstd for its own CG channels in its prologue and no separate kernel runs at all.
+struct Affine {
+    const float* scale;
+    const float* shift;
+    const float2* pa;     // [B][slots_a][Ca] (sum, sumsq); channels [0, Ca)
+    const float2* pb;     // [B][slots_b][Cb]; channels [Ca, Ca + Cb) (second half of a skip concat) | NULL
+    const float* gamma;
+    const float* beta;
+    int slots_a, Ca, slots_b, Cb, groups, HW;
+    float eps;
+};
+
+template <int CG>
+__device__ __forceinline__ void gn_prologue(const Affine& af, int b, int c0, int C, float* s_sc, float* s_sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cpg = C / af.groups;
+    const int slots_max = max(af.slots_a, af.slots_b);
+    for (int ch = warp; ch < CG; ch += nwarps) {
+        const int c = c0 + ch;
+        const int g = c / cpg;
+        double s = 0.0, q = 0.0;
+        for (int it = lane; it < slots_max * cpg; it += 32) {
+            const int sl = it / cpg, cc = g * cpg + (it - sl * cpg);
+            float2 v = make_float2(0.f, 0.f);
+            if (cc < af.Ca) {
+                if (sl < af.slots_a) v = af.pa[((size_t)b * af.slots_a + sl) * af.Ca + cc];
+            } else {
+                if (sl < af.slots_b) v = af.pb[((size_t)b * af.slots_b + sl) * af.Cb + (cc - af.Ca)];
+            }
+            s += (double)v.x;
+            q += (double)v.y;
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if (lane == 0) {
+            const double n = (double)af.HW * (double)cpg;
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)af.eps));
+            const float sc = (af.gamma != nullptr ? af.gamma[c] : 1.f) * rstd;
+            s_sc[ch] = sc;
+            s_sh[ch] = fmaf(-(float)mean, sc, af.beta != nullptr ? af.beta[c] : 0.f);
+        }
+    }
+    __syncthreads();
+}
+
 template <int N, int CG>
 struct Tile {
     static constexpr int PITCH = (2 * N + 1) * CG;  // floats per tile row (padded)
@@ -76,11 +126,12 @@ struct Tile {
 // N: side of the SMALL plane (input of FACT / UP2, output of DOWN2).
 template <int N, int CG, int MODE, int ACT>
 __global__ void __launch_bounds__(256, 2)
-resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
-                const float* __restrict__ scale, const float* __restrict__ shift) {
+resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const Affine af) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float tile[];
+    __shared__ float s_sc[CG], s_sh[CG];
+    if (MODE != MODE_DOWN2 && af.pa != nullptr) gn_prologue<CG>(af, blockIdx.y, blockIdx.x * CG, C, s_sc, s_sh);
     constexpr int PITCH = Tile<N, CG>::PITCH;
     constexpr int M = 2 * N;
     const int b = blockIdx.y;
@@ -91,9 +142,12 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
         for (int t = threadIdx.x; t < N * CG; t += blockDim.x) {
             const int c = t % CG, i = t / CG;
             float sc = 1.f, sh = 0.f;
-            if (scale != nullptr) {
-                sc = scale[(size_t)b * C + c0 + c];
-                sh = shift[(size_t)b * C + c0 + c];
+            if (af.pa != nullptr) {
+                sc = s_sc[c];
+                sh = s_sh[c];
+            } else if (af.scale != nullptr) {
+                sc = af.scale[(size_t)b * C + c0 + c];
+                sh = af.shift[(size_t)b * C + c0 + c];
             }
             const float* xp = x + ((size_t)(b * N + i) * N) * C + c0 + c;
             float xr[N], od[N];
@@ -204,11 +258,12 @@ __device__ __forceinline__ void down_rolled(float (&a)[2 * N], float* __restrict
 
 template <int N, int CG, int MODE, int ACT>
 __global__ void __launch_bounds__(256, 2)
-resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
-                       const float* __restrict__ scale, const float* __restrict__ shift) {
+resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const Affine af) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float tile[];
+    __shared__ float s_sc[CG], s_sh[CG];
+    if (MODE != MODE_DOWN2 && af.pa != nullptr) gn_prologue<CG>(af, blockIdx.y, blockIdx.x * CG, C, s_sc, s_sh);
     constexpr int PITCH = Tile<N, CG>::PITCH;
     constexpr int M = 2 * N;
     const int b = blockIdx.y;
@@ -232,9 +287,12 @@ resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C
                 float xr[N], od[N];
                 if (phv == 0) {
                     float sc = 1.f, sh = 0.f;
-                    if (scale != nullptr) {
-                        sc = scale[(size_t)b * C + c0 + c];
-                        sh = shift[(size_t)b * C + c0 + c];
+                    if (af.pa != nullptr) {
+                        sc = s_sc[c];
+                        sh = s_sh[c];
+                    } else if (af.scale != nullptr) {
+                        sc = af.scale[(size_t)b * C + c0 + c];
+                        sh = af.shift[(size_t)b * C + c0 + c];
                     }
                     const float* xp = x + ((size_t)(b * N + line) * N) * C + c0 + c;
 #pragma unroll
@@ -287,8 +345,7 @@ resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C
 }
 
 template <int N, int CG, int MODE, int ACT>
-int launch_one(const float* x, float* y, int B, int C, const float* scale, const float* shift,
-               cudaStream_t st) {
+int launch_one(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
     if (C % CG != 0) return AFLDM_E_SHAPE;
     auto kern = (N >= 32) ? resample_phased_kernel<N, CG, MODE, ACT> : resample_kernel<N, CG, MODE, ACT>;
     constexpr int smem = Tile<N, CG>::SMEM_BYTES;
@@ -300,21 +357,27 @@ int launch_one(const float* x, float* y, int B, int C, const float* scale, const
     }
     constexpr int tasks = 2 * N * CG;
     const int threads = tasks >= 256 ? 256 : (tasks < 32 ? 32 : tasks);
-    launch_k(kern, dim3(C / CG, B), dim3(threads), smem, st, x, y, C, scale, shift);
+    launch_k(kern, dim3(C / CG, B), dim3(threads), smem, st, x, y, C, af);
     return launched();
 }
 
 template <int MODE, int ACT>
-int dispatch_n(const float* x, float* y, int B, int n, int C, const float* scale, const float* shift,
-               cudaStream_t st) {
+int dispatch_n(const float* x, float* y, int B, int n, int C, const Affine& af, cudaStream_t st) {
     switch (n) {
-        case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
-        case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
-        case 8: return launch_one<8, 32, MODE, ACT>(x, y, B, C, scale, shift, st);
-        case 16: return launch_one<16, 16, MODE, ACT>(x, y, B, C, scale, shift, st);
-        case 32: return launch_one<32, 8, MODE, ACT>(x, y, B, C, scale, shift, st);
+        case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, af, st);
+        case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, af, st);
+        case 8: return launch_one<8, 32, MODE, ACT>(x, y, B, C, af, st);
+        case 16: return launch_one<16, 16, MODE, ACT>(x, y, B, C, af, st);
+        case 32: return launch_one<32, 8, MODE, ACT>(x, y, B, C, af, st);
         default: return AFLDM_E_NOKERNEL;
     }
+}
+
+Affine plain_affine(const float* scale, const float* shift) {
+    Affine af{};
+    af.scale = scale;
+    af.shift = shift;
+    return af;
 }
 
 bool bad_args(const float* x, const float* y, int B, int H, int W, int C, const float* scale,
@@ -341,8 +404,31 @@ extern "C" int afldm_filtered_act_f32(const float* x, float* y, int B, int H, in
     if (H != W) return AFLDM_E_SHAPE;  // the reference's mask is built from W only (ideal_lpf.py:81-88)
     cudaStream_t st = as_stream(stream);
     if (H > 32) return resample_large(MODE_FACT, act, x, y, B, H, C, scale, shift, workspace, workspace_floats, st);
-    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, scale, shift, st);
-    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
+    const Affine af = plain_affine(scale, shift);
+    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, af, st);
+    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, st);
+}
+
+extern "C" int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H, int W, int C, int act,
+                                         const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                         int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                         const float* beta, afldm_stream_t stream) {
+    if (bad_args(x, y, B, H, W, C, nullptr, nullptr) || partial_a == nullptr) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
+    if (slots_a <= 0 || Ca <= 0 || Cb < 0 || groups <= 0 || (Cb > 0 && (partial_b == nullptr || slots_b <= 0)))
+        return AFLDM_E_ARG;
+    if (Ca + Cb != C || C % groups != 0) return AFLDM_E_SHAPE;
+    if (H != W) return AFLDM_E_SHAPE;
+    if (H > 32) return AFLDM_E_NOKERNEL;    // large planes: afldm_groupnorm_finalize_f32 + afldm_filtered_act_f32
+    Affine af{};
+    af.pa = reinterpret_cast<const float2*>(partial_a);
+    af.pb = reinterpret_cast<const float2*>(partial_b);
+    af.gamma = gamma; af.beta = beta;
+    af.slots_a = slots_a; af.Ca = Ca; af.slots_b = Cb > 0 ? slots_b : 0; af.Cb = Cb;
+    af.groups = groups; af.HW = H * W; af.eps = eps;
+    cudaStream_t st = as_stream(stream);
+    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, af, st);
+    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, st);
 }
 
 extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
@@ -353,7 +439,7 @@ extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W
     cudaStream_t st = as_stream(stream);
     if (H > 32)
         return resample_large(MODE_UP2, AFLDM_ACT_IDENTITY, x, y, B, H, C, scale, shift, workspace, workspace_floats, st);
-    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, scale, shift, st);
+    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, plain_affine(scale, shift), st);
 }
 
 extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,
@@ -364,5 +450,5 @@ extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W
     if (H > 32)
         return resample_large(MODE_DOWN2, AFLDM_ACT_IDENTITY, x, y, B, H, C, nullptr, nullptr, workspace,
                               workspace_floats, st);
-    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, nullptr, nullptr, st);
+    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, plain_affine(nullptr, nullptr), st);
 }

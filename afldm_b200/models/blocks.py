@@ -25,9 +25,9 @@ from ..packing import conv_params, fused_linear_params
 def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module) -> torch.Tensor:
     """act(GroupNorm(x)) on NHWC x: statistics pass + one fused apply kernel.
     A ``WarpedNonlinearity`` (alias-free surgery) selects the filtered activation."""
-    scale, shift = ops.groupnorm_affine(x, norm.num_groups, norm.eps, norm.weight, norm.bias)
     if isinstance(nonlinearity, WarpedNonlinearity):
-        return ops.filtered_act(x, scale, shift, act=nonlinearity.act)
+        return ops.filtered_act_groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=nonlinearity.act)
+    scale, shift = ops.groupnorm_affine(x, norm.num_groups, norm.eps, norm.weight, norm.bias)
     return ops.affine_act(x, scale, shift, act=act_name(nonlinearity))
 
 

@@ -73,6 +73,15 @@ AFLDM_API int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int
                            const float* scale, const float* shift, float* workspace,
                            size_t workspace_floats, afldm_stream_t stream);
 
+/* The same with the GroupNorm finalised inside the kernel from the partial sums the producer of x emitted
+ * (afldm_conv2d_f32 gn_partial; channels [0,Ca) from partial_a, [Ca,Ca+Cb) from partial_b as in
+ * afldm_groupnorm_finalize_f32): GroupNorm -> filtered activation costs ONE launch and one pass over x.
+ * Planes up to 32 x 32 (AFLDM_E_NOKERNEL above: finalize + afldm_filtered_act_f32). */
+AFLDM_API int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H, int W, int C, int act,
+                                        const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                        int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                        const float* beta, afldm_stream_t stream);
+
 /* UpsampleRFFT(up=2).forward (afldm/af_libs/ideal_lpf.py:148-158), optional affine on load:
  * x NHWC [B,H,W,C] -> y NHWC [B,2H,2W,C]. */
 AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,

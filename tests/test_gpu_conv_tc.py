@@ -113,6 +113,19 @@ def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
     s0, t0 = ops.groupnorm_affine(y.clone(), 32, 1e-5, gamma, beta)          # clone drops the attribute
     torch.testing.assert_close(s1, s0, rtol=2e-5, atol=1e-6)
     torch.testing.assert_close(t1, t0, rtol=0, atol=2e-5)
+    if h <= 32:
+        # GroupNorm finalised inside the filtered-activation kernel == statistics pass + filtered activation
+        rec = []
+        ops.record_to(rec)
+        ops.FUSE_GN_PROLOGUE = True
+        try:
+            fa1 = ops.filtered_act_groupnorm(y, 32, 1e-5, gamma, beta)
+        finally:
+            ops.FUSE_GN_PROLOGUE = False
+            ops.record_to(None)
+        assert [r[0] for r in rec] == ["filtered_act"]                       # one launch
+        fa0 = ops.filtered_act(y, s0, t0)
+        torch.testing.assert_close(fa1, fa0, rtol=0, atol=3e-5)
     # through the zero-copy layout views and a channel concat of two producers
     v = ops.nhwc(ops.nchw_view(y))
     assert hasattr(v, "_afldm_gn")
@@ -124,3 +137,6 @@ def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
     sr, tr = ops.groupnorm_affine(cat.clone(), 32, 1e-5, g2, b2)
     torch.testing.assert_close(sc, sr, rtol=2e-5, atol=1e-6)
     torch.testing.assert_close(tc, tr, rtol=0, atol=2e-5)
+    if h <= 32:
+        torch.testing.assert_close(ops.filtered_act_groupnorm(cat, 32, 1e-5, g2, b2), ops.filtered_act(cat, sr, tr),
+                                   rtol=0, atol=3e-5)
