@@ -35,10 +35,12 @@ constexpr int TBM = 128;           // output pixels per tile (UMMA M)
 constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
 constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
-// All shared memory is dynamic: [stage ring | mbarriers + TMEM slot (SMEM_TAIL bytes)].  The epilogue's
-// staging tiles alias the (by then idle) stage ring, so the whole 227 KB goes to operands in flight.
-constexpr int SMEM_TAIL = 256;
-constexpr int SMEM_BUDGET = 224 * 1024;                          // stage ring, one CTA per SM
+// All shared memory is dynamic: [stage ring | epilogue staging | mbarriers + TMEM slot].  (The kernel is
+// persistent, so the epilogue of one tile overlaps the ring traffic of the next: staging cannot alias the ring.)
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 36 * 4;                 // 4 epilogue warps x 32 rows x (32 + 4) floats
+constexpr int GN_STAGE_BYTES = 4 * 192 * 8;                      // 4 epilogue warps x 192 columns x float2
+constexpr int SMEM_TAIL = EPI_STAGE_BYTES + GN_STAGE_BYTES + 256;   // staging + mbarriers + TMEM slot
+constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - SMEM_TAIL;       // stage ring, one CTA per SM
 constexpr int SMEM_TWO_PER_SM = (232448 / 2) - 1024 - SMEM_TAIL; // stage ring that lets two CTAs share an SM
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_PITCH = 36;
@@ -70,22 +72,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// Multicast variant: the box is written at the same shared-memory offset of every CTA in cta_mask and
-// completes bytes on the mbarrier at the same offset in each of them.
-__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                               int c2, int c3, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"(cta_mask)
         : "memory");
 }
 // ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256), each CTA stages its own 128 rows
@@ -194,16 +180,28 @@ struct TcArgs {
     int vec_ok;                     // all epilogue pointers / pitches allow float4 access
     float* gn_partial;              // [B][gn_slots][Cout] float2 GroupNorm partial sums of the output | NULL
     int gn_slots;
-    int cluster;                    // CTAs along N that share (multicast) one A tile: 1, 2 or 4
-    int slice_dim;                  // which box dim the A tile is sliced along for the multicast (1 = W, 2 = H, 3 = B)
-    int slice_step;                 // coordinate step between consecutive slices
+    int mtiles, ntiles, splitk;     // work items = mtiles * ntiles * splitk (pairs: mtiles / 2 M-tile pairs)
+    int nacc;                       // TMEM accumulator buffers (2: epilogue of item i overlaps main loop of i+1)
 };
 
-// TWO = false: one CTA per 128 x BN tile (cta_group::1).
-// TWO = true : a cluster of two CTAs (consecutive blockIdx.x = consecutive M tiles) computes 256 x BN with
-//              tcgen05.mma.cta_group::2 issued by the even CTA; each CTA stages 128 rows of A and BN/2 rows of B,
-//              i.e. 16 KB + BN*64 B per stage instead of 16 KB + BN*128 B - the SM's operand ingest (the measured
-//              bound of the main loop) buys up to 2x the FLOPs.
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {      // bar: shared::cluster address
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent, warp-specialised implicit-GEMM kernel.  Every CTA (TWO: every CTA pair) walks the work items
+// item = first, first + stride, ... ; an item is one 128 x BN (pair: 256 x BN) output tile of one K split.
+//   warp 0      TMA producer: A box per filter tap + B box into the stage ring (runs ahead across items)
+//   warp 1      MMA issuer (pair: only in the even CTA): tcgen05.mma into TMEM accumulator buffer (item % nacc)
+//   warps 2..5  epilogue: tcgen05.ld -> smem transpose -> coalesced float4 stores (+bias +temb row +residual),
+//               GroupNorm partial sums; releases the accumulator buffer back to the MMA warp
+// With two accumulator buffers the epilogue of item i runs under the main loop of item i + 1, and the TMEM
+// allocation, barrier init and tensor-map fetch are paid once per CTA instead of once per tile.
+// TWO = true: tcgen05.mma.cta_group::2 (M = 256) over a cluster of two CTAs; each CTA stages its own 128 rows
+// of A and BN/2 rows of B (16 KB + BN*64 B per stage instead of 16 KB + BN*128 B): the SM's operand ingest,
+// the measured bound of the main loop, buys up to 2x the FLOPs.
 template <bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -214,27 +212,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if ((smem_base & 1023u) != 0u) __trap();                 // swizzle-128B atoms need 1024 B alignment
     const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * TBK * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)a.stages * stage_bytes);
+    // layout: [stage ring][epilogue staging 4 x 32 x 36 floats][GroupNorm staging 4 x 192 float2][barriers]
+    uint8_t* const tail = smem_raw + (size_t)a.stages * stage_bytes;
+    float (*epi_stage)[32 * EPI_PITCH] = reinterpret_cast<float (*)[32 * EPI_PITCH]>(tail);
+    float2 (*gn_stage)[192] = reinterpret_cast<float2 (*)[192]>(tail + EPI_STAGE_BYTES);
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(tail + EPI_STAGE_BYTES + GN_STAGE_BYTES);
     uint64_t* const empty_bar = full_bar + MAX_STAGES;
-    uint64_t* const accum_bar_p = empty_bar + MAX_STAGES;
-    uint32_t* const tmem_slot_p = reinterpret_cast<uint32_t*>(accum_bar_p + 1);
-    // epilogue staging (aliases the stage ring, idle once the accumulator is complete):
-    //   per epilogue warp 32 rows x (32 + 4) floats (pitch 36: conflict-free both ways), then the
-    //   per-warp GroupNorm (sum, sumsq) of 32 rows per column
-    float (*epi_stage)[32 * EPI_PITCH] = reinterpret_cast<float (*)[32 * EPI_PITCH]>(smem_raw);
-    float2 (*gn_stage)[192] = reinterpret_cast<float2 (*)[192]>(smem_raw + 4 * 32 * EPI_PITCH * 4);
+    uint64_t* const acc_full = empty_bar + MAX_STAGES;       // [2]
+    uint64_t* const acc_empty = acc_full + 2;                // [2]
+    uint32_t* const tmem_slot_p = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int total_iters = a.taps * a.cin_chunks;
-    const int it_beg = blockIdx.z * a.iters_per_split;
-    const int it_end = min(total_iters, it_beg + a.iters_per_split);
-    const int n_iters = it_end - it_beg;
+    const uint32_t crank = TWO ? cluster_rank() : 0u;
+    const bool mma_leader = !TWO || crank == 0u;
+    // work items of this CTA (pair): first, first + stride, ...
+    const int n_items = (TWO ? a.mtiles / 2 : a.mtiles) * a.ntiles * a.splitk;
+    const int first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), (uint32_t)a.cluster);   // one MMA commit per CTA of the cluster
+            mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(accum_bar_p), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&acc_full[i]), 1);
+            mbar_init(smem_u32(&acc_empty[i]), TWO ? 8 : 4);     // one arrival per epilogue warp (of both CTAs)
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -257,203 +261,228 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (TWO || a.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+    if constexpr (TWO) cluster_sync_all();          // the peer's barriers exist before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_p;
-    const uint32_t crank = (TWO || a.cluster > 1) ? cluster_rank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << a.cluster) - 1u);
     // Everything above touched only this CTA's shared / tensor memory: it may overlap the tail of the
     // previous kernel on the stream.  From here on global memory is read.
     pdl_trigger();
     pdl_wait();
 
-    const int m0 = blockIdx.x * TBM;
-    const int n0 = blockIdx.y * a.BN;
-    const bool mma_leader = !TWO || crank == 0u;
+    // item -> (M tile, N tile, K split); N tile fastest so that concurrently running items share A in L2
+    auto decode = [&](int item, int& mt, int& nt, int& z) {
+        nt = item % a.ntiles;
+        const int r = item / a.ntiles;
+        const int mrow = TWO ? a.mtiles / 2 : a.mtiles;
+        const int mi = r % mrow;
+        z = r / mrow;
+        mt = TWO ? 2 * mi + (int)crank : mi;
+    };
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && n_iters > 0) {
-            // tile origin in (w, h, b)
-            int w0, h0, b0;
-            if (a.W >= TBM) {
-                const int per_row = a.W / TBM;
-                const int row = blockIdx.x / per_row;
-                w0 = (blockIdx.x % per_row) * TBM;
-                h0 = row % a.H;
-                b0 = row / a.H;
-            } else if (a.BH == a.H) {
-                w0 = 0; h0 = 0;
-                b0 = blockIdx.x * (TBM / (a.W * a.H));
-            } else {
-                const int per_img = a.H / a.BH;
-                w0 = 0;
-                h0 = (blockIdx.x % per_img) * a.BH;
-                b0 = blockIdx.x / per_img;
-            }
+        if (lane == 0) {
             const int pad = a.ks >> 1;
-            for (int i = 0; i < n_iters; ++i) {
-                const int s = i % a.stages;
-                const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
-                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                const int it = it_beg + i;
-                const int tap = it / a.cin_chunks;
-                const int c0 = (it - tap * a.cin_chunks) * TBK;
-                const int dh = tap / a.ks - pad, dw = tap % a.ks - pad;
-                const uint32_t fb = smem_u32(&full_bar[s]);
-                const uint32_t sa = smem_base + s * stage_bytes;
-                if constexpr (TWO) {
-                    // both CTAs' bytes complete on the leader's barrier; only the leader arms it
-                    if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
-                    tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
-                    tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
-                    continue;
-                }
-                mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                if (a.cluster == 1) {
-                    tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+            uint32_t g = 0;                                 // ring position, continues across items
+            for (int item = first; item < n_items; item += stride) {
+                int mt, nt, z;
+                decode(item, mt, nt, z);
+                int w0, h0, b0;                             // tile origin in (w, h, b)
+                if (a.W >= TBM) {
+                    const int per_row = a.W / TBM;
+                    const int row = mt / per_row;
+                    w0 = (mt % per_row) * TBM;
+                    h0 = row % a.H;
+                    b0 = row / a.H;
+                } else if (a.BH == a.H) {
+                    w0 = 0; h0 = 0;
+                    b0 = mt * (TBM / (a.W * a.H));
                 } else {
-                    // this CTA fetches slice `crank` of the shared A tile and multicasts it to the whole cluster
-                    const int off = (int)crank * a.slice_step;
-                    const int cw = w0 + dw + (a.slice_dim == 1 ? off : 0);
-                    const int chh = h0 + dh + (a.slice_dim == 2 ? off : 0);
-                    const int cb = b0 + (a.slice_dim == 3 ? off : 0);
-                    tma_load_4d_mc(sa + crank * (A_STAGE_BYTES / a.cluster), &map_a, fb, c0, cw, chh, cb, cmask);
+                    const int per_img = a.H / a.BH;
+                    w0 = 0;
+                    h0 = (mt % per_img) * a.BH;
+                    b0 = mt / per_img;
                 }
-                tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
+                const int n0 = nt * a.BN;
+                const int it_beg = z * a.iters_per_split;
+                const int it_end = min(total_iters, it_beg + a.iters_per_split);
+                for (int it = it_beg; it < it_end; ++it, ++g) {
+                    const int s = (int)(g % (uint32_t)a.stages);
+                    const uint32_t ph = (g / (uint32_t)a.stages) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const int tap = it / a.cin_chunks;
+                    const int c0 = (it - tap * a.cin_chunks) * TBK;
+                    const int dh = tap / a.ks - pad, dw = tap % a.ks - pad;
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    if constexpr (TWO) {
+                        // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+                        if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
+                        tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                        tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
+                    } else {
+                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                        tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                        tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && n_iters > 0 && mma_leader) {
+        if (lane == 0 && mma_leader) {
             // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both,
             // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
                                    ((uint32_t)((TWO ? 2 * TBM : TBM) >> 4) << 24);
-            for (int i = 0; i < n_iters; ++i) {
-                const int s = i % a.stages;
-                const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
+            uint32_t g = 0;
+            int j = 0;                                      // local item counter
+            for (int item = first; item < n_items; item += stride, ++j) {
+                int mt, nt, z;
+                decode(item, mt, nt, z);
+                const int it_beg = z * a.iters_per_split;
+                const int n_it = min(total_iters, it_beg + a.iters_per_split) - it_beg;
+                const int ab = j % a.nacc;
+                const uint32_t aph = (uint32_t)(j / a.nacc) & 1u;
+                mbar_wait(smem_u32(&acc_empty[ab]), aph ^ 1u);      // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_base + s * stage_bytes;
-                const uint64_t da = make_desc(sa), db = make_desc(sa + A_STAGE_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * a.BN);
+                for (int i = 0; i < n_it; ++i, ++g) {
+                    const int s = (int)(g % (uint32_t)a.stages);
+                    const uint32_t ph = (g / (uint32_t)a.stages) & 1u;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint64_t da = make_desc(sa), db = make_desc(sa + A_STAGE_BYTES);
 #pragma unroll
-                for (int k = 0; k < TBK / UMMA_K; ++k) {
-                    // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                    if constexpr (TWO) umma2_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
-                    else umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < TBK / UMMA_K; ++k) {
+                        // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                        if constexpr (TWO) umma2_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                        else umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                    }
+                    // frees the stage (in both CTAs of a pair) when these MMAs retire
+                    if constexpr (TWO) umma2_commit_mc(smem_u32(&empty_bar[s]), 3);
+                    else umma_commit(smem_u32(&empty_bar[s]));
                 }
-                // frees the stage (in every CTA that writes into it) when these MMAs retire
-                if constexpr (TWO) umma2_commit_mc(smem_u32(&empty_bar[s]), 3);
-                else if (a.cluster == 1) umma_commit(smem_u32(&empty_bar[s]));
-                else umma_commit_mc(smem_u32(&empty_bar[s]), cmask);
+                // accumulator complete (in both CTAs of a pair)
+                if constexpr (TWO) umma2_commit_mc(smem_u32(&acc_full[ab]), 3);
+                else umma_commit(smem_u32(&acc_full[ab]));
             }
-            // accumulator complete (in both CTAs of a pair)
-            if constexpr (TWO) umma2_commit_mc(smem_u32(accum_bar_p), 3);
-            else umma_commit(smem_u32(accum_bar_p));
         }
     } else {
         // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
         const int q = warp & 3;
-        const bool split = gridDim.z > 1;
-        if (n_iters > 0) {
-            mbar_wait(smem_u32(accum_bar_p), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
+        const bool split = a.splitk > 1;
         float* stg = epi_stage[q];
         const int cq = lane & 7, rsub = lane >> 3;      // coalesced phase: 8 lanes x float4 per row, 4 rows per pass
-        for (int c = 0; c < a.BN; c += 32) {
-            uint32_t r[32];
-            if (n_iters > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        int j = 0;
+        for (int item = first; item < n_items; item += stride, ++j) {
+            int mt, nt, z;
+            decode(item, mt, nt, z);
+            const int m0 = mt * TBM, n0 = nt * a.BN;
+            const int ab = j % a.nacc;
+            const uint32_t aph = (uint32_t)(j / a.nacc) & 1u;
+            mbar_wait(smem_u32(&acc_full[ab]), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * a.BN);
+            for (int c = 0; c < a.BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tacc + (uint32_t)c, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            // each thread owns one accumulator row: park it in the staging tile ...
-            float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            __syncwarp();
-            // ... and write it out 4 rows x 128 contiguous bytes per instruction
-            const int n = n0 + c + cq * 4;
-            float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-                const int rr = pass * 4 + rsub;
-                const int mm = m0 + q * 32 + rr;
-                if (mm >= a.M || n >= a.Cout || c + cq * 4 >= a.BN) continue;
-                float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + cq * 4);
-                if (split) {
-                    *reinterpret_cast<float4*>(a.ws + ((size_t)blockIdx.z * a.M + mm) * a.Cout + n) = v;
-                } else if (a.vec_ok) {
-                    if (a.bias != nullptr) {
-                        const float4 t = *reinterpret_cast<const float4*>(a.bias + n);
-                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                    }
-                    if (a.row_add != nullptr) {
-                        const float4 t = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n);
-                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                    }
-                    if (a.residual != nullptr) {
-                        const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
-                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                    }
-                    *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
-                    gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
-                    gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
-                    gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
-                } else {
-                    float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (n + j >= a.Cout) break;
-                        float t = e[j];
-                        if (a.bias != nullptr) t += a.bias[n + j];
-                        if (a.row_add != nullptr) t += a.row_add[(size_t)(mm / a.HW) * a.row_add_pitch + n + j];
-                        if (a.residual != nullptr) t += a.residual[(size_t)mm * a.res_pitch + n + j];
-                        a.y[(size_t)mm * a.y_pitch + n + j] = t;
+                if (c + 32 >= a.BN) {
+                    // last read of this accumulator: hand it back to the MMA warp before the stores go out
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (TWO) mbar_arrive_cluster(smem_u32(&acc_empty[ab]) & PEER_BIT_MASK);
+                        else mbar_arrive_local(smem_u32(&acc_empty[ab]));
                     }
                 }
+                // each thread owns one accumulator row: park it in the staging tile ...
+                float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    srow[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                           __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+                __syncwarp();
+                // ... and write it out 4 rows x 128 contiguous bytes per instruction
+                const int n = n0 + c + cq * 4;
+                float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int rr = pass * 4 + rsub;
+                    const int mm = m0 + q * 32 + rr;
+                    if (mm >= a.M || n >= a.Cout || c + cq * 4 >= a.BN) continue;
+                    float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + cq * 4);
+                    if (split) {
+                        *reinterpret_cast<float4*>(a.ws + ((size_t)z * a.M + mm) * a.Cout + n) = v;
+                    } else if (a.vec_ok) {
+                        if (a.bias != nullptr) {
+                            const float4 t = *reinterpret_cast<const float4*>(a.bias + n);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        if (a.row_add != nullptr) {
+                            const float4 t = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        if (a.residual != nullptr) {
+                            const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
+                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        }
+                        *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
+                        gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
+                        gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
+                        gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
+                    } else {
+                        float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            if (n + jj >= a.Cout) break;
+                            float t = e[jj];
+                            if (a.bias != nullptr) t += a.bias[n + jj];
+                            if (a.row_add != nullptr) t += a.row_add[(size_t)(mm / a.HW) * a.row_add_pitch + n + jj];
+                            if (a.residual != nullptr) t += a.residual[(size_t)mm * a.res_pitch + n + jj];
+                            a.y[(size_t)mm * a.y_pitch + n + jj] = t;
+                        }
+                    }
+                }
+                if (a.gn_partial != nullptr) {
+                    // rows live in lanes rsub = 0..3 of the same column quad: fold them, lanes 0..7 keep the totals
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        gs[jj] += __shfl_xor_sync(0xffffffffu, gs[jj], 8);
+                        gq[jj] += __shfl_xor_sync(0xffffffffu, gq[jj], 8);
+                        gs[jj] += __shfl_xor_sync(0xffffffffu, gs[jj], 16);
+                        gq[jj] += __shfl_xor_sync(0xffffffffu, gq[jj], 16);
+                    }
+                    if (rsub == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) gn_stage[q][c + cq * 4 + jj] = make_float2(gs[jj], gq[jj]);
+                    }
+                }
+                __syncwarp();
             }
             if (a.gn_partial != nullptr) {
-                // rows live in lanes rsub = 0..3 of the same column quad: fold them, lanes 0..7 keep the totals
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 8);
-                    gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 8);
-                    gs[j] += __shfl_xor_sync(0xffffffffu, gs[j], 16);
-                    gq[j] += __shfl_xor_sync(0xffffffffu, gq[j], 16);
+                // combine the four row quarters (fixed order) and publish one partial per (tile, channel)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int et = threadIdx.x - 64;            // 0..127 over the epilogue warps
+                const int bimg = m0 / a.HW;
+                const int slot = (m0 - bimg * a.HW) / TBM;
+                for (int col = et; col < a.BN; col += 128) {
+                    const int n = n0 + col;
+                    if (n >= a.Cout) continue;
+                    const float2 p0 = gn_stage[0][col], p1 = gn_stage[1][col], p2 = gn_stage[2][col], p3 = gn_stage[3][col];
+                    reinterpret_cast<float2*>(a.gn_partial)[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
+                        make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
                 }
-                if (rsub == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) gn_stage[q][c + cq * 4 + j] = make_float2(gs[j], gq[j]);
-                }
-            }
-            __syncwarp();
-        }
-        if (a.gn_partial != nullptr) {
-            // combine the four row quarters (fixed order) and publish one partial per (tile, channel)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int et = threadIdx.x - 64;            // 0..127 over the epilogue warps
-            const int bimg = m0 / a.HW;
-            const int slot = (m0 - bimg * a.HW) / TBM;
-            for (int col = et; col < a.BN; col += 128) {
-                const int n = n0 + col;
-                if (n >= a.Cout) continue;
-                const float2 p0 = gn_stage[0][col], p1 = gn_stage[1][col], p2 = gn_stage[2][col], p3 = gn_stage[3][col];
-                reinterpret_cast<float2*>(a.gn_partial)[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
-                    make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // staging is reused by the next item
             }
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (TWO || a.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
+    if constexpr (TWO) cluster_sync_all();          // no CTA leaves while its peer may still signal it
     if (warp == 1) {
         if constexpr (TWO)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
@@ -484,11 +513,22 @@ EncodeTiledFn encode_fn() {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+int num_sms() {
+    static const int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;     // B200
+        return v;
+    }();
+    return n;
+}
+
 struct TcPlan {
     bool ok;
     int M, mtiles, ntiles, BN, stages, tmem_cols, total_iters, splitk, iters_per_split, BW, BH, BB;
-    int cluster, slice_dim, slice_step, slice_box[3];   // A-tile multicast across N-tile CTAs
     int two;                                            // CTA-pair (cta_group::2) mode
+    int ctas_per_sm, grid_ctas, nacc;                   // persistent grid and TMEM accumulator buffers
     size_t smem_bytes;
 };
 
@@ -579,26 +619,19 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     const int budget = two_per_sm ? SMEM_TWO_PER_SM : SMEM_BUDGET;
     p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
     if (force_stages > 0) p.stages = std::min(force_stages, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
-    p.stages = std::min(p.stages, std::max(2, p.iters_per_split));
-    p.smem_bytes = (size_t)p.stages * stage_bytes + SMEM_TAIL;
+    // Persistent grid: one or two CTAs per SM walk the work items; two TMEM accumulator buffers when they fit
+    // (512 columns per SM) so that an item's epilogue runs under the next item's main loop.
+    p.ctas_per_sm = two_per_sm ? 2 : 1;
+    const int items = (p.two ? p.mtiles / 2 : p.mtiles) * p.ntiles * p.splitk;
+    const int slots = num_sms() * p.ctas_per_sm;
+    if (p.two) p.grid_ctas = 2 * std::min(items, slots / 2);
+    else p.grid_ctas = std::min(items, slots);
+    p.nacc = (2 * p.BN * p.ctas_per_sm <= 512 && items > (p.two ? p.grid_ctas / 2 : p.grid_ctas)) ? 2 : 1;
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
-    // A-tile multicast (opt-in, AFLDM_TC_CLUSTER=2|4): CTAs of the same M tile (consecutive blockIdx.y) form a
-    // cluster; each fetches 1/CL of the 128-pixel A box and multicasts it, cutting the L2 reads of A by CL.
-    // Measured on B200 (profiles/r01_conv_notes.md): no gain - the main loop is bound by bytes in flight per SM
-    // (shared-memory capacity x L2 latency), not by L2 bandwidth, and the cluster couples the CTAs' pipelines.
-    static const int force_cluster = getenv("AFLDM_TC_CLUSTER") ? atoi(getenv("AFLDM_TC_CLUSTER")) : -1;
-    int cl = 1;
-    if (force_cluster >= 1 && p.splitk == 1 && !p.two) cl = (p.ntiles % force_cluster == 0 && (force_cluster == 1 || force_cluster == 2 || force_cluster == 4)) ? force_cluster : 1;
-    p.slice_box[0] = p.BW; p.slice_box[1] = p.BH; p.slice_box[2] = p.BB;
-    p.slice_dim = 0; p.slice_step = 0;
-    while (cl > 1) {
-        if (p.BB > 1 && p.BB % cl == 0) { p.slice_dim = 3; p.slice_step = p.BB / cl; p.slice_box[2] = p.BB / cl; break; }
-        if (p.BB == 1 && p.BH > 1 && p.BH % cl == 0) { p.slice_dim = 2; p.slice_step = p.BH / cl; p.slice_box[1] = p.BH / cl; break; }
-        if (p.BB == 1 && p.BH == 1 && p.BW % cl == 0) { p.slice_dim = 1; p.slice_step = p.BW / cl; p.slice_box[0] = p.BW / cl; break; }
-        cl >>= 1;
-    }
-    p.cluster = cl;
+    while (p.tmem_cols < p.nacc * p.BN) p.tmem_cols <<= 1;
+    const int items_per_cta = ceil_div(items, p.two ? p.grid_ctas / 2 : p.grid_ctas);
+    p.stages = std::min(p.stages, std::max(2, p.iters_per_split * items_per_cta));   // never more than there is to load
+    p.smem_bytes = (size_t)p.stages * stage_bytes + SMEM_TAIL;
     p.ok = true;
     return p;
 }
@@ -638,8 +671,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * W,
                                        (cuuint64_t)x_pitch * 4 * W * H};
-        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.slice_box[0], (cuuint32_t)p.slice_box[1],
-                                   (cuuint32_t)p.slice_box[2]};
+        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BB};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -681,8 +713,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
-    a.cluster = p.cluster; a.slice_dim = p.slice_dim; a.slice_step = p.slice_step;
-    dim3 grid(p.mtiles, p.ntiles, p.splitk);
+    a.mtiles = p.mtiles; a.ntiles = p.ntiles; a.splitk = p.splitk; a.nacc = p.nacc;
+    dim3 grid(p.grid_ctas, 1, 1);
     if (p.two) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid;
@@ -697,22 +729,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, map_a, map_b, a);
-    } else if (p.cluster == 1) {
-        launch_k(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
     } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = p.smem_bytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1;
-        attr[0].val.clusterDim.y = (unsigned)p.cluster;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, map_a, map_b, a);
+        launch_k(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
     }
     int launches = 1;
     if (p.splitk > 1) {
