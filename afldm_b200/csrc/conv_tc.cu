@@ -39,9 +39,10 @@ constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
 // persistent, so the epilogue of one tile overlaps the ring traffic of the next: staging cannot alias the ring.)
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 36 * 4;                 // 4 epilogue warps x 32 rows x (32 + 4) floats
 constexpr int GN_STAGE_BYTES = 4 * 192 * 8;                      // 4 epilogue warps x 192 columns x float2
-constexpr int SMEM_TAIL = EPI_STAGE_BYTES + GN_STAGE_BYTES + 256;   // staging + mbarriers + TMEM slot
-constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - SMEM_TAIL;       // stage ring, one CTA per SM
-constexpr int SMEM_TWO_PER_SM = (232448 / 2) - 1024 - SMEM_TAIL; // stage ring that lets two CTAs share an SM
+constexpr int STAGING_BYTES = EPI_STAGE_BYTES + GN_STAGE_BYTES;  // epilogue staging (aliases the ring when a CTA runs one item)
+constexpr int BARRIER_BYTES = 256;                               // mbarriers + TMEM slot
+constexpr int SMEM_ONE_PER_SM = 232448 - 1024 - BARRIER_BYTES;       // ring (+ staging), one CTA per SM
+constexpr int SMEM_TWO_PER_SM = (232448 / 2) - 1024 - BARRIER_BYTES; // ring (+ staging), two CTAs per SM
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_PITCH = 36;
 constexpr int TC_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
@@ -182,6 +183,7 @@ struct TcArgs {
     int gn_slots;
     int mtiles, ntiles, splitk;     // work items = mtiles * ntiles * splitk (pairs: mtiles / 2 M-tile pairs)
     int nacc;                       // TMEM accumulator buffers (2: epilogue of item i overlaps main loop of i+1)
+    int alias_staging;              // one item per CTA: the epilogue staging reuses the (then idle) stage ring
 };
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
@@ -213,10 +215,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * TBK * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
     // layout: [stage ring][epilogue staging 4 x 32 x 36 floats][GroupNorm staging 4 x 192 float2][barriers]
-    uint8_t* const tail = smem_raw + (size_t)a.stages * stage_bytes;
-    float (*epi_stage)[32 * EPI_PITCH] = reinterpret_cast<float (*)[32 * EPI_PITCH]>(tail);
-    float2 (*gn_stage)[192] = reinterpret_cast<float2 (*)[192]>(tail + EPI_STAGE_BYTES);
-    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(tail + EPI_STAGE_BYTES + GN_STAGE_BYTES);
+    uint8_t* const ring_end = smem_raw + (size_t)a.stages * stage_bytes;
+    uint8_t* const staging = a.alias_staging ? smem_raw : ring_end;
+    float (*epi_stage)[32 * EPI_PITCH] = reinterpret_cast<float (*)[32 * EPI_PITCH]>(staging);
+    float2 (*gn_stage)[192] = reinterpret_cast<float2 (*)[192]>(staging + EPI_STAGE_BYTES);
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(ring_end + (a.alias_staging ? 0 : STAGING_BYTES));
     uint64_t* const empty_bar = full_bar + MAX_STAGES;
     uint64_t* const acc_full = empty_bar + MAX_STAGES;       // [2]
     uint64_t* const acc_empty = acc_full + 2;                // [2]
@@ -269,13 +272,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     pdl_trigger();
     pdl_wait();
 
-    // item -> (M tile, N tile, K split); N tile fastest so that concurrently running items share A in L2
+    // item -> (M tile, N tile, K split).  M fastest: neighbouring CTAs (and the two CTAs sharing an SM) work on
+    // neighbouring pixel tiles with the same weight tile, as in the 2-D grid this kernel grew out of.
     auto decode = [&](int item, int& mt, int& nt, int& z) {
-        nt = item % a.ntiles;
-        const int r = item / a.ntiles;
         const int mrow = TWO ? a.mtiles / 2 : a.mtiles;
-        const int mi = r % mrow;
-        z = r / mrow;
+        const int mi = item % mrow;
+        const int r = item / mrow;
+        nt = r % a.ntiles;
+        z = r / a.ntiles;
         mt = TWO ? 2 * mi + (int)crank : mi;
     };
 
@@ -528,7 +532,7 @@ struct TcPlan {
     bool ok;
     int M, mtiles, ntiles, BN, stages, tmem_cols, total_iters, splitk, iters_per_split, BW, BH, BB;
     int two;                                            // CTA-pair (cta_group::2) mode
-    int ctas_per_sm, grid_ctas, nacc;                   // persistent grid and TMEM accumulator buffers
+    int ctas_per_sm, grid_ctas, nacc, alias_staging;    // persistent grid and TMEM accumulator buffers
     size_t smem_bytes;
 };
 
@@ -615,23 +619,24 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     const int tiles2 = p.mtiles * p.ntiles;
     // More CTAs than SMs and a small stage: size the ring so that two CTAs share an SM and one CTA's
     // prologue / epilogue hides behind the other's main loop.
-    const bool two_per_sm = tiles2 * p.splitk > 148 && 3 * stage_bytes <= SMEM_TWO_PER_SM;
-    const int budget = two_per_sm ? SMEM_TWO_PER_SM : SMEM_BUDGET;
-    p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
-    if (force_stages > 0) p.stages = std::min(force_stages, std::min(MAX_STAGES, SMEM_BUDGET / stage_bytes));
+    const int items = (p.two ? p.mtiles / 2 : p.mtiles) * p.ntiles * p.splitk;
+    const bool two_per_sm = tiles2 * p.splitk > num_sms() && 3 * stage_bytes + STAGING_BYTES <= SMEM_TWO_PER_SM;
     // Persistent grid: one or two CTAs per SM walk the work items; two TMEM accumulator buffers when they fit
     // (512 columns per SM) so that an item's epilogue runs under the next item's main loop.
     p.ctas_per_sm = two_per_sm ? 2 : 1;
-    const int items = (p.two ? p.mtiles / 2 : p.mtiles) * p.ntiles * p.splitk;
     const int slots = num_sms() * p.ctas_per_sm;
     if (p.two) p.grid_ctas = 2 * std::min(items, slots / 2);
     else p.grid_ctas = std::min(items, slots);
-    p.nacc = (2 * p.BN * p.ctas_per_sm <= 512 && items > (p.two ? p.grid_ctas / 2 : p.grid_ctas)) ? 2 : 1;
+    const int items_per_cta = ceil_div(items, p.two ? p.grid_ctas / 2 : p.grid_ctas);
+    p.alias_staging = items_per_cta == 1;
+    p.nacc = (2 * p.BN * p.ctas_per_sm <= 512 && items_per_cta > 1) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.nacc * p.BN) p.tmem_cols <<= 1;
-    const int items_per_cta = ceil_div(items, p.two ? p.grid_ctas / 2 : p.grid_ctas);
+    const int budget = (two_per_sm ? SMEM_TWO_PER_SM : SMEM_ONE_PER_SM) - (p.alias_staging ? 0 : STAGING_BYTES);
+    p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
+    if (force_stages > 0) p.stages = std::max(2, std::min(force_stages, p.stages));
     p.stages = std::min(p.stages, std::max(2, p.iters_per_split * items_per_cta));   // never more than there is to load
-    p.smem_bytes = (size_t)p.stages * stage_bytes + SMEM_TAIL;
+    p.smem_bytes = (size_t)p.stages * stage_bytes + (p.alias_staging ? 0 : STAGING_BYTES) + BARRIER_BYTES;
     p.ok = true;
     return p;
 }
@@ -693,10 +698,10 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM_BUDGET + SMEM_TAIL);
+                                             SMEM_ONE_PER_SM + BARRIER_BYTES);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_BUDGET + SMEM_TAIL);
+                                 SMEM_ONE_PER_SM + BARRIER_BYTES);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -714,6 +719,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
     a.mtiles = p.mtiles; a.ntiles = p.ntiles; a.splitk = p.splitk; a.nacc = p.nacc;
+    a.alias_staging = p.alias_staging;
     dim3 grid(p.grid_ctas, 1, 1);
     if (p.two) {
         cudaLaunchConfig_t cfg{};
