@@ -35,6 +35,15 @@ BATCH = 16
 WORKLOAD = "FFHQ AF-LDM UNet2DModel (256.4M params, make_af_unet), latents 16x4x32x32 per GPU, DDIM eta=0"
 
 
+def ncu_traffic(kind):
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return float(json.load(open(p))[kind]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -348,13 +357,15 @@ def main():
         if a["flops"] > 0:
             ach = a["flops"] / (a["ms"] / 1e3) / 1e12
             roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_sustained"], "traffic": None, "launches_per_step": a["launches"],
+                        "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(name), "launches_per_step": a["launches"],
                         "avg_launch_ms": a["ms"] / a["launches"],
-                        "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step's launch mix)"}
+                        "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step's launch mix); "
+                                       "operands are TF32, whose tensor peak is half the bf16 peak",
+                        "algorithmic_flops_per_step": a["flops"], "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)"}
         else:
             ach = a["bytes"] / (a["ms"] / 1e3) / 1e9
             roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": None, "launches_per_step": a["launches"],
+                        "frac": ach / pk["hbm"], "traffic": ncu_traffic(name), "launches_per_step": a["launches"],
                         "avg_launch_ms": a["ms"] / a["launches"], "peak_source": pk["source"]}
         fa = agg.get("filtered_act")
         if fa:
