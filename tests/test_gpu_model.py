@@ -192,6 +192,48 @@ def test_afvae_decode_and_encode_vs_oracle():
         torch.testing.assert_close(m_got, m_want, rtol=0, atol=2e-4)
 
 
+def test_i2sb_bridge_matches_oracle():
+    """Config #5 path on a small UNet: the I2SB sampling loop (i2sb_pipeline.py:45-56), ODE mode."""
+    from afldm_b200.pipelines import I2SBLDMPipeline
+    from afldm_b200.schedulers import I2SBScheduler
+    from oracle.i2sb import I2SBScheduler as RefSched
+    mine, ref = _small_unets(seed=4)
+    pipe = I2SBLDMPipeline(None, mine, I2SBScheduler.from_config())
+    x = randn(2, 4, 16, 16, seed=21)
+    got = pipe.bridge(x, num_inference_steps=6, is_ode=True)
+    rs = RefSched()
+    rs.set_timesteps(6)
+    lat = x
+    with torch.no_grad():
+        for i, t in enumerate(rs.timesteps):
+            if i == 5:
+                break
+            lat = rs.step(ref(lat, t.to(DEV)).sample, int(t), lat, is_ode=True, return_dict=False)[0]
+    torch.testing.assert_close(got, lat, rtol=0, atol=1e-3)
+
+
+def test_ldm_pipeline_call_end_to_end():
+    """MyLDMPipeline.__call__ (ldm_pipeline.py:32-131): latents -> DDIM (CUDA graph) -> alias-free VAE decode."""
+    from afldm_b200.models import AliasFreeAutoencoderKL
+    mine, _ = _small_unets(seed=5)
+    torch.manual_seed(1)
+    vae = AliasFreeAutoencoderKL.from_config(block_out_channels=[32, 64], down_block_types=["DownEncoderBlock2D"] * 2,
+                                             up_block_types=["UpDecoderBlock2D"] * 2, layers_per_block=1,
+                                             down_filtered_act=[False, True], up_filtered_act=[True, False],
+                                             up_rescale=[True]).to(DEV).eval()
+    pipe = MyLDMPipeline(vae, mine, DDIMScheduler.from_config())
+    g = torch.Generator().manual_seed(3)
+    img = pipe(batch_size=2, generator=g, num_inference_steps=3, output_type="pt")
+    assert img.shape == (2, 3, 32, 32) and torch.isfinite(img).all()
+    g = torch.Generator().manual_seed(3)
+    out = pipe(batch_size=2, generator=g, num_inference_steps=3, output_type="np")
+    assert out.images.shape == (2, 32, 32, 3) and out.images.min() >= 0 and out.images.max() <= 1
+    lat = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=3, output_type="latent")
+    eager = pipe(batch_size=2, generator=torch.Generator().manual_seed(3), num_inference_steps=3, output_type="latent",
+                 use_cuda_graph=False)
+    assert torch.equal(lat, eager)
+
+
 @pytest.mark.slow
 def test_full_ffhq_unet_step_vs_oracle():
     """BASELINE config #2 architecture (256.4 M parameters), B = 2, one forward."""

@@ -145,3 +145,29 @@ def test_pack_conv_weight_layout():
     p = ops.pack_conv_weight(w)
     assert p.shape == (2, 9, 3)
     assert p[1, 5, 2] == w[1, 2, 1, 2]          # tap (kh=1, kw=2) -> index 5, channel last
+
+
+def test_i2sb_schedule_matches_oracle():
+    """I2SB scheduler scalars (i2sb_scheduler.py:188-197, 382-459): the collapsed one-kernel update
+    x_prev = x + c_eps * eps equals the reference's mu_x0 * x0 + mu_xt * x_t formulation."""
+    from afldm_b200.schedulers import I2SBScheduler
+    from oracle.i2sb import I2SBScheduler as Ref
+    mine, ref = I2SBScheduler.from_config(), Ref()
+    mine.set_timesteps(100)
+    ref.set_timesteps(100)
+    assert mine.timesteps.tolist() == ref.timesteps.tolist() and mine.timesteps[0] == 991
+    assert torch.equal(mine.std_fwd, ref.std_fwd) and torch.equal(mine.mu_x0, ref.mu_x0)
+    g = torch.Generator().manual_seed(0)
+    x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    for t in (991, 501, 21, 11):
+        c_eps, sqrt_var = mine.coefficients(t)
+        want = ref.step(e, t, x, is_ode=True, return_dict=False)[0]
+        torch.testing.assert_close(x + c_eps * e, want, rtol=0, atol=2e-6)
+        g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+        want_sde = ref.step(e, t, x, is_ode=False, generator=g1, return_dict=False)[0]
+        noise = torch.randn(e.shape, generator=g2)
+        torch.testing.assert_close(x + c_eps * e + sqrt_var * noise, want_sde, rtol=0, atol=2e-6)
+    x1 = torch.randn(2, 4, 8, 8, generator=g)
+    ts = torch.tensor([10, 700])
+    torch.testing.assert_close(mine.add_noise(x, x1, ts, is_ode=True), ref.add_noise(x, x1, ts, is_ode=True))
+    torch.testing.assert_close(mine.compute_label(ts, x, x1), ref.compute_label(ts, x, x1))
