@@ -162,7 +162,17 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int D>
+__device__ __forceinline__ float ex2_approx(float x) {      // 2^x, one MUFU; -inf -> 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// MT = 16-row query tiles per warp: 2 for long sequences (every K / V fragment read from shared memory feeds
+// two MMAs; ncu on the MT = 1 version showed ~700 issued instructions per 48 HMMA, profiles/r02_ncu_attention.md),
+// 1 for short ones (more CTAs).  K fragments are read as 64-bit words: MMA k-index t <- head-dim column 2t,
+// t + 4 <- 2t + 1 inside each 8-column chunk, the Q fragment uses the same permutation.
+template <int D, int MT>
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
                      const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
@@ -170,34 +180,38 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
     pdl_trigger();
     pdl_wait();
     constexpr int KT = 64;            // keys per tile
-    constexpr int P = D + 4;          // smem row pitch (words)
+    constexpr int PK = (D % 32 == 8) ? D : ((D / 32) * 32 + 40);   // K row pitch (words), = 8 mod 32: conflict-free 64-bit fragment loads
+    constexpr int P = D + 4;          // V row pitch (words): conflict-free 32-bit fragment loads
     constexpr int DK = D / 8;         // k-steps of Q.K^T == n-tiles of P.V
     constexpr int D4 = D / 4;
     // double-buffered K / V tiles: tile i+1 streams in with cp.async while tile i is consumed
-    extern __shared__ __align__(16) float att_smem[];          // [K0 | K1 | V0 | V1], each KT * P floats
-    auto Kbuf = [&](int i) { return att_smem + i * (KT * P); };
-    auto Vbuf = [&](int i) { return att_smem + (2 + i) * (KT * P); };
+    extern __shared__ __align__(16) float att_smem[];          // [K0 | K1 | V0 | V1]
+    auto Kbuf = [&](int i) { return att_smem + i * (KT * PK); };
+    auto Vbuf = [&](int i) { return att_smem + 2 * (KT * PK) + i * (KT * P); };
     const int b = blockIdx.z, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int bkv = b / Bkv_rep;
-    const int row0 = blockIdx.x * 64 + warp * 16 + g;      // this lane's rows: row0 and row0 + 8
-    const int row1 = row0 + 8;
+    const int wrow = blockIdx.x * (64 * MT) + warp * (16 * MT);     // first query row of this warp
 
     const float* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
     const float* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
     auto load_tile = [&](int buf, int k0) {
         const int nk = min(KT, Nk - k0);
-        for (int idx = threadIdx.x; idx < KT * D4; idx += blockDim.x) {
+        float* kb = Kbuf(buf);
+        float* vb = Vbuf(buf);
+#pragma unroll
+        for (int it = 0; it < (KT * D4 + 127) / 128; ++it) {
+            const int idx = it * 128 + threadIdx.x;
+            if (idx >= KT * D4) break;
             const int key = idx / D4, c4 = idx - key * D4;
-            float* kd = Kbuf(buf) + key * P + 4 * c4;
-            float* vd = Vbuf(buf) + key * P + 4 * c4;
+            float* kd = kb + key * PK + 4 * c4;
+            float* vd = vb + key * P + 4 * c4;
             if (key < nk) {
                 const uint32_t ks_ = (uint32_t)__cvta_generic_to_shared(kd), vs_ = (uint32_t)__cvta_generic_to_shared(vd);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_),
-                             "l"(kbase + (size_t)(k0 + key) * kv_pitch + 4 * c4) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_),
-                             "l"(vbase + (size_t)(k0 + key) * kv_pitch + 4 * c4) : "memory");
+                const size_t goff = (size_t)(k0 + key) * kv_pitch + 4 * c4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_), "l"(kbase + goff) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_), "l"(vbase + goff) : "memory");
             } else {
                 *reinterpret_cast<float4*>(kd) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(vd) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,25 +221,34 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
     };
     load_tile(0, 0);
 
-    // Q fragments (scaled into the exp2 domain, rounded to TF32 once)
-    uint32_t qa[DK][4];
-    {
-        const float* q0 = q + ((size_t)b * Nq + min(row0, Nq - 1)) * q_pitch + head * D;
-        const float* q1 = q + ((size_t)b * Nq + min(row1, Nq - 1)) * q_pitch + head * D;
+    // Q fragments (scaled into the exp2 domain, rounded to TF32 once); permuted k order (see above)
+    uint32_t qa[MT][DK][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = wrow + mt * 16 + g, r1 = r0 + 8;
+        const float* q0 = q + ((size_t)b * Nq + min(r0, Nq - 1)) * q_pitch + head * D + 2 * t;
+        const float* q1 = q + ((size_t)b * Nq + min(r1, Nq - 1)) * q_pitch + head * D + 2 * t;
 #pragma unroll
         for (int ks = 0; ks < DK; ++ks) {
-            qa[ks][0] = to_tf32(q0[8 * ks + t] * qscale);
-            qa[ks][1] = to_tf32(q1[8 * ks + t] * qscale);
-            qa[ks][2] = to_tf32(q0[8 * ks + t + 4] * qscale);
-            qa[ks][3] = to_tf32(q1[8 * ks + t + 4] * qscale);
+            const float2 a0 = *reinterpret_cast<const float2*>(q0 + 8 * ks);
+            const float2 a1 = *reinterpret_cast<const float2*>(q1 + 8 * ks);
+            qa[mt][ks][0] = to_tf32(a0.x * qscale);
+            qa[mt][ks][1] = to_tf32(a1.x * qscale);
+            qa[mt][ks][2] = to_tf32(a0.y * qscale);
+            qa[mt][ks][3] = to_tf32(a1.y * qscale);
         }
     }
-    float oacc[DK][4];
+    float oacc[MT][DK][4];
+    float mrun[MT][2], lrun[MT][2];
 #pragma unroll
-    for (int i = 0; i < DK; ++i)
+    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        for (int i = 0; i < DK; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oacc[mt][i][j] = 0.f;
+        mrun[mt][0] = mrun[mt][1] = -INFINITY;
+        lrun[mt][0] = lrun[mt][1] = 0.f;
+    }
 
     int buf = 0;
     for (int k0 = 0; k0 < Nk; k0 += KT, buf ^= 1) {
@@ -241,88 +264,126 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
         const float* Vt = Vbuf(buf);
 
         // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
-        float s[8][4];
+        float s[MT][8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            const float* kr = &Kt[(nt * 8 + g) * P + t];
 #pragma unroll
-            for (int ks = 0; ks < DK; ++ks)
-                mma_tf32(s[nt], qa[ks], __float_as_uint(kr[8 * ks]), __float_as_uint(kr[8 * ks + 4]));
+            for (int mt = 0; mt < MT; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+            const float* kr = &Kt[(nt * 8 + g) * PK + 2 * t];
+#pragma unroll
+            for (int ks = 0; ks < DK; ++ks) {
+                const float2 kb = *reinterpret_cast<const float2*>(kr + 8 * ks);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(s[mt][nt], qa[mt][ks], __float_as_uint(kb.x), __float_as_uint(kb.y));
+            }
         }
-        // mask the tail keys, row maxima over the tile
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (nk < KT) {                  // only the last tile of a ragged sequence has keys to mask
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int key = nt * 8 + 2 * t;
-            if (key >= nk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-            if (key + 1 >= nk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            for (int nt = 0; nt < 8; ++nt) {
+                const int key = nt * 8 + 2 * t;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (key >= nk) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
+                    if (key + 1 >= nk) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+                }
+            }
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);      // finite: key k0 is always valid
-        const float c0 = exp2f(m0 - n0), c1 = exp2f(m1 - n1);
-        m0 = n0; m1 = n1;
-        l0 *= c0; l1 *= c1;
+        float nm[MT][2];
 #pragma unroll
-        for (int dn = 0; dn < DK; ++dn) {
-            oacc[dn][0] *= c0; oacc[dn][1] *= c0;
-            oacc[dn][2] *= c1; oacc[dn][3] *= c1;
+        for (int mt = 0; mt < MT; ++mt) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float n0 = fmaxf(mrun[mt][0], mx0), n1 = fmaxf(mrun[mt][1], mx1);   // finite: key k0 is always valid
+            const float c0 = ex2_approx(mrun[mt][0] - n0), c1 = ex2_approx(mrun[mt][1] - n1);
+            mrun[mt][0] = n0; mrun[mt][1] = n1;
+            nm[mt][0] = n0; nm[mt][1] = n1;
+            lrun[mt][0] *= c0; lrun[mt][1] *= c1;
+#pragma unroll
+            for (int dn = 0; dn < DK; ++dn) {
+                oacc[mt][dn][0] *= c0; oacc[mt][dn][1] *= c0;
+                oacc[mt][dn][2] *= c1; oacc[mt][dn][3] *= c1;
+            }
         }
         // P = exp2(S - m); O += P V
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const float p00 = exp2f(s[nt][0] - n0), p01 = exp2f(s[nt][1] - n0);
-            const float p10 = exp2f(s[nt][2] - n1), p11 = exp2f(s[nt][3] - n1);
-            l0 += p00 + p01;
-            l1 += p10 + p11;
-            // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
-            const uint32_t pa[4] = {to_tf32(p00), to_tf32(p10), to_tf32(p01), to_tf32(p11)};
+            uint32_t pa[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const float p00 = ex2_approx(s[mt][nt][0] - nm[mt][0]), p01 = ex2_approx(s[mt][nt][1] - nm[mt][0]);
+                const float p10 = ex2_approx(s[mt][nt][2] - nm[mt][1]), p11 = ex2_approx(s[mt][nt][3] - nm[mt][1]);
+                lrun[mt][0] += p00 + p01;
+                lrun[mt][1] += p10 + p11;
+                // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
+                pa[mt][0] = to_tf32(p00); pa[mt][1] = to_tf32(p10); pa[mt][2] = to_tf32(p01); pa[mt][3] = to_tf32(p11);
+            }
             const float* vr0 = &Vt[(nt * 8 + 2 * t) * P + g];
             const float* vr1 = vr0 + P;
 #pragma unroll
-            for (int dn = 0; dn < DK; ++dn)
-                mma_tf32(oacc[dn], pa, __float_as_uint(vr0[8 * dn]), __float_as_uint(vr1[8 * dn]));
+            for (int dn = 0; dn < DK; ++dn) {
+                const uint32_t b0 = __float_as_uint(vr0[8 * dn]), b1 = __float_as_uint(vr1[8 * dn]);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(oacc[mt][dn], pa[mt], b0, b1);
+            }
         }
         __syncthreads();                                       // everyone is done with `buf` before it is refilled
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    if (row0 < Nq) {
-        float* op = o + ((size_t)b * Nq + row0) * o_pitch + head * D + 2 * t;
 #pragma unroll
-        for (int dn = 0; dn < DK; ++dn)
-            *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[dn][0] * i0, oacc[dn][1] * i0);
-    }
-    if (row1 < Nq) {
-        float* op = o + ((size_t)b * Nq + row1) * o_pitch + head * D + 2 * t;
+    for (int mt = 0; mt < MT; ++mt) {
+        float l0 = lrun[mt][0], l1 = lrun[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = wrow + mt * 16 + g, r1 = r0 + 8;
+        if (r0 < Nq) {
+            float* op = o + ((size_t)b * Nq + r0) * o_pitch + head * D + 2 * t;
 #pragma unroll
-        for (int dn = 0; dn < DK; ++dn)
-            *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[dn][2] * i1, oacc[dn][3] * i1);
+            for (int dn = 0; dn < DK; ++dn)
+                *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[mt][dn][0] * i0, oacc[mt][dn][1] * i0);
+        }
+        if (r1 < Nq) {
+            float* op = o + ((size_t)b * Nq + r1) * o_pitch + head * D + 2 * t;
+#pragma unroll
+            for (int dn = 0; dn < DK; ++dn)
+                *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[mt][dn][2] * i1, oacc[mt][dn][3] * i1);
+        }
     }
+}
+
+template <int D, int MT>
+int launch_mma_mt(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
+                  int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+    const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
+    constexpr int PK = (D % 32 == 8) ? D : ((D / 32) * 32 + 40);
+    constexpr int smem = 2 * 64 * (PK + D + 4) * 4;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+    launch_k(attention_mma_kernel<D, MT>, dim3(ceil_div(Nq, 64 * MT), heads, B), dim3(128), smem, st,
+        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
+    return launched();
 }
 
 template <int D>
 int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
                int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
-    const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
-    constexpr int smem = 4 * 64 * (D + 4) * 4;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    configured = true;
-    launch_k(attention_mma_kernel<D>, dim3(ceil_div(Nq, 64), heads, B), dim3(128), smem, st, 
-        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
-    return launched();
+    // two query tiles per warp once there are enough CTAs left to fill the chip twice over
+    if (D <= 32 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
+        return launch_mma_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
 }
 
 template <int D>

@@ -184,7 +184,19 @@ struct TcArgs {
     int mtiles, ntiles, splitk;     // work items = mtiles * ntiles * splitk (pairs: mtiles / 2 M-tile pairs)
     int nacc;                       // TMEM accumulator buffers (2: epilogue of item i overlaps main loop of i+1)
     int alias_staging;              // one item per CTA: the epilogue staging reuses the (then idle) stage ring
+    int halo;                       // 3x3 halo mode: one A box {32 ch, BW, BH + 2} per (kw, channel chunk) serves the 3 kh taps
 };
+
+// One lane of a converged warp (elect.sync); the same lane every time for the full mask.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -204,16 +216,23 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {      // bar:
 // TWO = true: tcgen05.mma.cta_group::2 (M = 256) over a cluster of two CTAs; each CTA stages its own 128 rows
 // of A and BN/2 rows of B (16 KB + BN*64 B per stage instead of 16 KB + BN*128 B): the SM's operand ingest,
 // the measured bound of the main loop, buys up to 2x the FLOPs.
-template <bool TWO>
+template <bool TWO, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static smem: the ring starts 1024-aligned
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0u) __trap();                 // swizzle-128B atoms need 1024 B alignment
     const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * TBK * 4;
-    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    // Halo mode (3x3, tile = BH >= 2 whole image rows): a stage holds the box of BH + 2 rows shifted by kw - 1
+    // and the three weight tiles of taps (kh, kw), kh = 0..2.  Tap kh reads the SAME box BW rows further down
+    // (a multiple of the 1024 B swizzle atom, so only the descriptor start address moves): the SM ingests
+    // 3 (BH + 2) / (9 BH) of the activation bytes of the one-box-per-tap scheme - the measured bound of the
+    // main loop is operand bytes staged per SM (profiles/r01_conv_notes.md).
+    const int a_bytes = HALO ? (a.BH + 2) * a.BW * TBK * 4 : A_STAGE_BYTES;
+    constexpr int nb = HALO ? 3 : 1;
+    const int stage_bytes = a_bytes + nb * b_stage_bytes;
     // layout: [stage ring][epilogue staging 4 x 32 x 36 floats][GroupNorm staging 4 x 192 float2][barriers]
     uint8_t* const ring_end = smem_raw + (size_t)a.stages * stage_bytes;
     uint8_t* const staging = a.alias_staging ? smem_raw : ring_end;
@@ -283,11 +302,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mt = TWO ? 2 * mi + (int)crank : mi;
     };
 
+    // The producer and the MMA issuer run their loops with the WHOLE warp (warp-uniform control flow) and elect one
+    // lane only around the TMA / tcgen05 instructions.  Under `if (lane == 0)` the compiler cannot keep descriptors,
+    // barrier addresses and coordinates in uniform registers and wraps every UTCHMMA / UTMALDG in an
+    // ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY waterfall (~15 instructions per 32..48-cycle MMA, ncu / SASS of the
+    // r01 kernel); ring position and tap / chunk counters are carried incrementally instead of divided out.
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        {
             const int pad = a.ks >> 1;
-            uint32_t g = 0;                                 // ring position, continues across items
+            int s = 0;                                      // ring slot and its phase, continue across items
+            uint32_t ph = 0;
             for (int item = first; item < n_items; item += stride) {
                 int mt, nt, z;
                 decode(item, mt, nt, z);
@@ -310,67 +335,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int n0 = nt * a.BN;
                 const int it_beg = z * a.iters_per_split;
                 const int it_end = min(total_iters, it_beg + a.iters_per_split);
-                for (int it = it_beg; it < it_end; ++it, ++g) {
-                    const int s = (int)(g % (uint32_t)a.stages);
-                    const uint32_t ph = (g / (uint32_t)a.stages) & 1u;
+                int tap = it_beg / a.cin_chunks;
+                int chunk = it_beg - tap * a.cin_chunks;
+                for (int it = it_beg; it < it_end; ++it) {
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    const int tap = it / a.cin_chunks;
-                    const int c0 = (it - tap * a.cin_chunks) * TBK;
-                    const int dh = tap / a.ks - pad, dw = tap % a.ks - pad;
+                    const int c0 = chunk * TBK;
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     const uint32_t sa = smem_base + s * stage_bytes;
-                    if constexpr (TWO) {
-                        // both CTAs' bytes complete on the leader's barrier; only the leader arms it
-                        if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
-                        tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
-                        tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
-                    } else {
-                        mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                        tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
-                        tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
+                    if (elect_one()) {
+                        if constexpr (HALO) {
+                            // `tap` is kw here; weights are packed [Cout][kh * 3 + kw][Cin]
+                            const int nb0 = n0 + (TWO ? (int)crank * (a.BN / 2) : 0);
+                            const int kb = (tap * a.cin_chunks + chunk) * TBK;       // + kh * 3 * Cin
+                            const int kstep = 3 * a.cin_chunks * TBK;
+                            if constexpr (TWO) {
+                                if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
+                                tma2_load_4d(sa, &map_a, fb, c0, w0 + tap - 1, h0 - 1, b0);
+#pragma unroll
+                                for (int kh = 0; kh < 3; ++kh)
+                                    tma2_load_2d(sa + a_bytes + kh * b_stage_bytes, &map_b, fb, kb + kh * kstep, nb0);
+                            } else {
+                                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                                tma_load_4d(sa, &map_a, fb, c0, w0 + tap - 1, h0 - 1, b0);
+#pragma unroll
+                                for (int kh = 0; kh < 3; ++kh)
+                                    tma_load_2d(sa + a_bytes + kh * b_stage_bytes, &map_b, fb, kb + kh * kstep, nb0);
+                            }
+                        } else {
+                            const int th = tap / a.ks;
+                            const int dh = th - pad, dw = tap - th * a.ks - pad;
+                            if constexpr (TWO) {
+                                // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+                                if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
+                                tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                                tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
+                            } else {
+                                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                                tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                                tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (++chunk == a.cin_chunks) { chunk = 0; ++tap; }
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && mma_leader) {
+        if (mma_leader) {
             // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both,
             // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
                                    ((uint32_t)((TWO ? 2 * TBM : TBM) >> 4) << 24);
-            uint32_t g = 0;
-            int j = 0;                                      // local item counter
-            for (int item = first; item < n_items; item += stride, ++j) {
+            int s = 0;
+            uint32_t ph = 0;
+            int ab = 0;                                     // accumulator buffer of this item and its phase
+            uint32_t aph = 0;
+            for (int item = first; item < n_items; item += stride) {
                 int mt, nt, z;
                 decode(item, mt, nt, z);
                 const int it_beg = z * a.iters_per_split;
                 const int n_it = min(total_iters, it_beg + a.iters_per_split) - it_beg;
-                const int ab = j % a.nacc;
-                const uint32_t aph = (uint32_t)(j / a.nacc) & 1u;
                 mbar_wait(smem_u32(&acc_empty[ab]), aph ^ 1u);      // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(ab * a.BN);
-                for (int i = 0; i < n_it; ++i, ++g) {
-                    const int s = (int)(g % (uint32_t)a.stages);
-                    const uint32_t ph = (g / (uint32_t)a.stages) & 1u;
+                for (int i = 0; i < n_it; ++i) {
                     mbar_wait(smem_u32(&full_bar[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t sa = smem_base + s * stage_bytes;
-                    const uint64_t da = make_desc(sa), db = make_desc(sa + A_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TBK / UMMA_K; ++k) {
-                        // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-                        if constexpr (TWO) umma2_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
-                        else umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, (i | k) != 0 ? 1u : 0u);
+                        for (int kh = 0; kh < nb; ++kh) {
+                            // halo mode: tap kh = the same box, BW pixel rows (BW * 128 B) further down
+                            const uint64_t da = make_desc(sa + (HALO ? (uint32_t)(kh * a.BW * TBK * 4) : 0u));
+                            const uint64_t db = make_desc(sa + (uint32_t)a_bytes + (uint32_t)(kh * b_stage_bytes));
+#pragma unroll
+                            for (int k = 0; k < TBK / UMMA_K; ++k) {
+                                // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                                const uint32_t acc = (i | kh | k) != 0 ? 1u : 0u;
+                                if constexpr (TWO) umma2_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                else umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                            }
+                        }
+                        // frees the stage (in both CTAs of a pair) when these MMAs retire
+                        if constexpr (TWO) umma2_commit_mc(smem_u32(&empty_bar[s]), 3);
+                        else umma_commit(smem_u32(&empty_bar[s]));
+                        // accumulator complete (in both CTAs of a pair); same lane as the MMAs (commit tracks the
+                        // issuing thread's tcgen05 operations)
+                        if (i == n_it - 1) {
+                            if constexpr (TWO) umma2_commit_mc(smem_u32(&acc_full[ab]), 3);
+                            else umma_commit(smem_u32(&acc_full[ab]));
+                        }
                     }
-                    // frees the stage (in both CTAs of a pair) when these MMAs retire
-                    if constexpr (TWO) umma2_commit_mc(smem_u32(&empty_bar[s]), 3);
-                    else umma_commit(smem_u32(&empty_bar[s]));
+                    __syncwarp();
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
                 }
-                // accumulator complete (in both CTAs of a pair)
-                if constexpr (TWO) umma2_commit_mc(smem_u32(&acc_full[ab]), 3);
-                else umma_commit(smem_u32(&acc_full[ab]));
+                if (++ab == a.nacc) { ab = 0; aph ^= 1u; }
             }
         }
     } else {
@@ -533,6 +595,7 @@ struct TcPlan {
     int M, mtiles, ntiles, BN, stages, tmem_cols, total_iters, splitk, iters_per_split, BW, BH, BB;
     int two;                                            // CTA-pair (cta_group::2) mode
     int ctas_per_sm, grid_ctas, nacc, alias_staging;    // persistent grid and TMEM accumulator buffers
+    int halo;                                           // 3x3 halo mode (one A box per kw and channel chunk)
     size_t smem_bytes;
 };
 
@@ -615,12 +678,24 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
             p.ntiles = Cout / bn2;
         }
     }
-    const int stage_bytes = A_STAGE_BYTES + (p.two ? p.BN / 2 : p.BN) * TBK * 4;
+    // Halo mode: un-split 3x3 layers whose 128-pixel tile is BH >= 2 whole rows of one image (W = 16 ... 64).
+    static const int allow_halo = getenv("AFLDM_TC_HALO") ? atoi(getenv("AFLDM_TC_HALO")) : 1;
+    // Not for the widest CTA-pair tiles: those layers already run tensor-bound (fewest bytes per FLOP) and the
+    // 60 KB halo stages leave a 3-deep ring (sweep on B200, profiles/r02_conv_halo_sweep.md: 68.9 vs 63.2 us).
+    p.halo = (allow_halo && ks == 3 && p.splitk == 1 && p.BB == 1 && p.BH >= 2 && p.BW >= 8 && p.BW * p.BH == TBM &&
+              !(p.two && p.BN >= 192 && allow_halo < 2)) ? 1 : 0;
+    const int b_bytes = (p.two ? p.BN / 2 : p.BN) * TBK * 4;
+    const int stage_bytes = p.halo ? (p.BH + 2) * p.BW * TBK * 4 + 3 * b_bytes : A_STAGE_BYTES + b_bytes;
+    if (p.halo) {
+        p.total_iters = 3 * (Cin / TBK);          // one stage per (kw, channel chunk): 12 MMAs
+        p.iters_per_split = p.total_iters;
+    }
     const int tiles2 = p.mtiles * p.ntiles;
     // More CTAs than SMs and a small stage: size the ring so that two CTAs share an SM and one CTA's
     // prologue / epilogue hides behind the other's main loop.
     const int items = (p.two ? p.mtiles / 2 : p.mtiles) * p.ntiles * p.splitk;
-    const bool two_per_sm = tiles2 * p.splitk > num_sms() && 3 * stage_bytes + STAGING_BYTES <= SMEM_TWO_PER_SM;
+    const int min_stages = p.halo ? 2 : 3;        // a halo stage carries three taps
+    const bool two_per_sm = tiles2 * p.splitk > num_sms() && min_stages * stage_bytes + STAGING_BYTES <= SMEM_TWO_PER_SM;
     // Persistent grid: one or two CTAs per SM walk the work items; two TMEM accumulator buffers when they fit
     // (512 columns per SM) so that an item's epilogue runs under the next item's main loop.
     p.ctas_per_sm = two_per_sm ? 2 : 1;
@@ -676,7 +751,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * W,
                                        (cuuint64_t)x_pitch * 4 * W * H};
-        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BB};
+        const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)(p.halo ? p.BH + 2 : p.BH), (cuuint32_t)p.BB};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -697,19 +772,21 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
 
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM_ONE_PER_SM + BARRIER_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_ONE_PER_SM + BARRIER_BYTES);
-        if (e != cudaSuccess) return (int)e;
+        cudaError_t e = cudaSuccess;
+        const void* kerns[4] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<false, true>,
+                                (const void*)conv_tc_kernel<true, false>, (const void*)conv_tc_kernel<true, true>};
+        for (const void* kp : kerns) {
+            e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ONE_PER_SM + BARRIER_BYTES);
+            if (e != cudaSuccess) return (int)e;
+        }
         configured = true;
     }
     TcArgs a;
     a.bias = bias; a.row_add = row_add; a.residual = residual; a.y = y; a.ws = workspace;
     a.row_add_pitch = row_add_pitch; a.res_pitch = res_pitch; a.y_pitch = y_pitch;
     a.M = p.M; a.Cout = Cout; a.HW = H * W;
-    a.taps = ks * ks; a.ks = ks; a.cin_chunks = Cin / TBK;
+    a.taps = p.halo ? 3 : ks * ks; a.ks = ks; a.cin_chunks = Cin / TBK;
+    a.halo = p.halo;
     a.iters_per_split = p.iters_per_split;
     a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
@@ -734,9 +811,12 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, map_a, map_b, a);
+        if (p.halo) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_b, a);
+        else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_b, a);
+    } else if (p.halo) {
+        launch_k(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
     } else {
-        launch_k(conv_tc_kernel<false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
+        launch_k(conv_tc_kernel<false, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
     }
     int launches = 1;
     if (p.splitk > 1) {

@@ -47,17 +47,34 @@ __device__ __forceinline__ void up_odd(const float (&x)[N], float (&o)[N]) {
     }
 }
 
-// y[i] = sum_m g[(2i - m) mod 2N] a[m]
+// y[i] = sum_m g[(2i - m) mod 2N] a[m].
+// The even-indexed taps of g need no convolution: the pass band of LPF_RFFT(.5) on 2N points is the N - 1
+// bins |k| < N/2 (create_lpf_rect zeroes bin N/2, ideal_lpf.py:12-24), so
+//      g[2r] = (1/2N) sum_{|k| < N/2} e^{2 pi i k r / N} = (1/2) delta[r mod N] - (-1)^r / (2N),
+// i.e. the even samples contribute  a[2i] / 2 - (-1)^i S / (2N)  with  S = sum_m (-1)^m a[2m]  (O(N) per
+// line); only the odd samples go through an N-tap circular convolution.  2N^2 -> N^2 + 2N FMAs per line.
+template <int N>
+__device__ __forceinline__ float alt_sum_even(const float (&a)[2 * N]) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < N; m += 2) {
+        s0 += a[2 * m];
+        s1 += a[2 * m + 2];
+    }
+    return (s0 - s1) * (1.0f / (2 * N));
+}
+
 template <int N>
 __device__ __forceinline__ void down_line(const float (&a)[2 * N], float (&y)[N]) {
     constexpr int IB = N >= 8 ? 8 : N;
+    const float sc = alt_sum_even<N>(a);
 #pragma unroll
     for (int i0 = 0; i0 < N; i0 += IB) {
         float acc[IB];
 #pragma unroll
-        for (int u = 0; u < IB; ++u) acc[u] = 0.f;
+        for (int u = 0; u < IB; ++u) acc[u] = fmaf(0.5f, a[2 * (i0 + u)], ((i0 + u) & 1) ? sc : -sc);
 #pragma unroll
-        for (int m = 0; m < 2 * N; ++m) {
+        for (int m = 1; m < 2 * N; m += 2) {
 #pragma unroll
             for (int u = 0; u < IB; ++u)
                 acc[u] = fmaf(tap_g<N>((2 * (i0 + u) - m) & (2 * N - 1)), a[m], acc[u]);
@@ -228,13 +245,14 @@ template <int N>
 __device__ __forceinline__ void down_rolled(float (&a)[2 * N], float* __restrict__ sdst, float* __restrict__ gdst,
                                             int stride, bool to_smem) {
     constexpr int M = 2 * N;
+    const float sc = alt_sum_even<N>(a);     // rotation-invariant: the line is rotated by multiples of 16
 #pragma unroll 1
     for (int blk = 0; blk < N / 8; ++blk) {
         float acc[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+        for (int u = 0; u < 8; ++u) acc[u] = fmaf(0.5f, a[2 * u], (u & 1) ? sc : -sc);
 #pragma unroll
-        for (int m = 0; m < M; ++m) {
+        for (int m = 1; m < M; m += 2) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc[u] = fmaf(tap_g<N>((2 * u - m) & (M - 1)), a[m], acc[u]);
         }

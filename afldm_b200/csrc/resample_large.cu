@@ -9,7 +9,7 @@
 // 8 at a time in registers, and the taps - indexed by a warp-uniform run-time value - come from
 // constant memory (15 loads per 64 FMAs).  The down-sampler uses its polyphase form
 //      y[i] = sum_s ge[s] Ae[i - s] + go[s] Ao[i - s - 1],   Ae = a[0::2], Ao = a[1::2],
-// so that it is two such convolutions of length n.
+// of which only the odd phase is a convolution of length n: ge is delta/2 minus a rank-one alternating term.
 //
 // This is the exact-fp32 SIMT path: correct for every supported n, FMA-bound.  (A tensor-core
 // formulation with split operands is the planned replacement for the VAE-sized planes.)
@@ -122,11 +122,18 @@ line_kernel(const LineArgs a) {
     }
     // polyphase down: Ae = A[0..N), Ao = (OP_DOWN ? A[N..2N) : Bq[0..N))
     const float* Ao = (OP == OP_DOWN) ? (A + (size_t)N * S) : Bq;
+    // even phase without a convolution: ge[r] = delta[r] / 2 - (-1)^r / (2N)  (pass band = bins |k| < N/2, see
+    // resample.cu down_line), so  sum_s ge[s] Ae[i - s] = Ae[i] / 2 - (-1)^i * altsum(Ae) / (2N)
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = 0; j < N; j += 2) {
+        s0 += A[j * S];
+        s1 += A[(j + 1) * S];
+    }
+    const float scorr = (s0 - s1) * (1.0f / (2 * N));
     for (int i0 = 0; i0 < N; i0 += 8) {
         float acc[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-        circ8<N, TAB_GE>(acc, A, S, i0, 0);
+        for (int u = 0; u < 8; ++u) acc[u] = fmaf(0.5f, A[(i0 + u) * S], (u & 1) ? scorr : -scorr);
         circ8<N, TAB_GO>(acc, Ao, S, i0, 1);
 #pragma unroll
         for (int u = 0; u < 8; ++u) yout[(i0 + u) * a.out_pos] = acc[u];

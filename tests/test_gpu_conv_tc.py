@@ -39,6 +39,9 @@ TC_CASES = [  # B, H, W, Cin, Cout, k      (every conv family of the FFHQ UNet +
     (16, 8, 8, 384, 384, 3), (3, 4, 4, 768, 768, 3), (16, 2, 2, 1536, 768, 3), (16, 2, 2, 768, 2304, 1),
     (1, 64, 64, 128, 128, 3), (1, 128, 128, 64, 32, 3), (1, 256, 256, 32, 16, 3), (5, 1, 1, 64, 64, 1),
     (2, 1024, 1, 192, 384, 1), (16, 32, 32, 192, 4, 3), (1, 64, 64, 128, 3, 3), (2, 16, 16, 64, 8, 1),
+    # halo-mode 3x3 layers (one activation box per kw serves three taps) at full batch: CTA pairs and single CTAs
+    (16, 16, 16, 384, 384, 3), (16, 16, 16, 768, 384, 3), (16, 32, 32, 384, 384, 3), (16, 16, 16, 192, 384, 3),
+    (8, 64, 64, 64, 64, 3),
 ]
 
 

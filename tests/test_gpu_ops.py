@@ -288,6 +288,14 @@ def test_linear_rows_and_timestep_embedding():
                                F.silu(F.linear(F.silu(x), w, bias)), rtol=0, atol=2e-5)
     x3 = randn(3, 192, seed=4)
     torch.testing.assert_close(ops.linear_rows(x3, w[:, :192].contiguous(), None), F.linear(x3, w[:, :192]), rtol=0, atol=2e-5)
+    # ragged shapes: N not a multiple of the 4 columns a warp owns (vector path), K % 4 != 0 (scalar path), M > 16
+    w2, b2 = randn(1001, 768, seed=5) * 0.03, randn(1001, seed=6)
+    torch.testing.assert_close(ops.linear_rows(x, w2, b2), F.linear(x, w2, b2), rtol=0, atol=2e-5)
+    x5, w5 = randn(5, 190, seed=7), randn(37, 190, seed=8) * 0.05
+    torch.testing.assert_close(ops.linear_rows(x5, w5, None), F.linear(x5, w5), rtol=0, atol=2e-5)
+    x20 = randn(20, 256, seed=9)
+    torch.testing.assert_close(ops.linear_rows(x20, w[:, :256].contiguous(), bias, act_out="silu"),
+                               F.silu(F.linear(x20, w[:, :256], bias)), rtol=0, atol=2e-5)
 
 
 def test_layout_concat_axpby_softmax():
