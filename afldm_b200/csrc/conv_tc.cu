@@ -670,6 +670,10 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
             for (int bn : c2)
                 if (Cout % bn == 0) { bn2 = bn; break; }              // very large layer: widest tile
         }
+        // 3x3 layers that run in halo mode (below): 96 columns.  With the activation bytes cut by the halo box the
+        // weight half-tile dominates the ingest, and 96 beats both 64 (more weight bytes per FLOP) and 128 / 192
+        // (60 KB stages, 3-deep ring) on every 16x16 / 32x32 layer of the step (profiles/r02_conv_knobs.md).
+        if (ks == 3 && p.BB == 1 && p.BH >= 2 && Cout % 96 == 0) bn2 = 96;
         if (ks != 3 && bn2 < 128) bn2 = 0;
         if (force_bn2 > 0) bn2 = (Cout % force_bn2 == 0 && force_bn2 % 16 == 0 && force_bn2 <= 256) ? force_bn2 : 0;
         if (bn2 > 0) {

@@ -19,6 +19,10 @@
 //
 // Algorithmic HBM traffic: filtered_act 8 B/element, up2 20 B per input element,
 // lpf_down2 5 B per input element (fp32).
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "resample.cuh"
 #include "taps.inc"
@@ -96,40 +100,62 @@ struct Affine {
     const float* beta;
     int slots_a, Ca, slots_b, Cb, groups, HW;
     float eps;
+    double inv_n;         // 1 / (HW * channels per group), from the host: no fp64 division in the prologue
 };
 
+// One warp per GroupNorm group touched by this CTA's CG channels (at most CG of them): the partial sums are added
+// in fp32 (they are fp32 sums over <= 128 pixels already), only the final E[x^2] - mean^2 is formed in fp64.
+// (The first version ran a full fp64 reduction per CHANNEL in every CTA and lost 5 us per call to the separate
+// finalize kernel; this one adds ~1 us of latency to the first wave of CTAs and removes a 3 us launch.)
 template <int CG>
 __device__ __forceinline__ void gn_prologue(const Affine& af, int b, int c0, int C, float* s_sc, float* s_sh) {
+    __shared__ float s_mean[CG], s_rstd[CG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int cpg = C / af.groups;
+    const int g_first = c0 / cpg, g_last = (c0 + CG - 1) / cpg;
     const int slots_max = max(af.slots_a, af.slots_b);
-    for (int ch = warp; ch < CG; ch += nwarps) {
-        const int c = c0 + ch;
-        const int g = c / cpg;
-        double s = 0.0, q = 0.0;
-        for (int it = lane; it < slots_max * cpg; it += 32) {
-            const int sl = it / cpg, cc = g * cpg + (it - sl * cpg);
-            float2 v = make_float2(0.f, 0.f);
-            if (cc < af.Ca) {
-                if (sl < af.slots_a) v = af.pa[((size_t)b * af.slots_a + sl) * af.Ca + cc];
-            } else {
-                if (sl < af.slots_b) v = af.pb[((size_t)b * af.slots_b + sl) * af.Cb + (cc - af.Ca)];
+    for (int gi = warp; gi <= g_last - g_first; gi += nwarps) {
+        const int g = g_first + gi;
+        float s = 0.f, q = 0.f;
+        const int total = slots_max * cpg;
+        for (int it0 = lane; it0 < total; it0 += 128) {      // four independent loads in flight per lane
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + 32 * u;
+                const int sl = it / cpg, cc = g * cpg + (it - sl * cpg);
+                v[u] = make_float2(0.f, 0.f);
+                if (it < total) {
+                    if (cc < af.Ca) {
+                        if (sl < af.slots_a) v[u] = __ldg(&af.pa[((size_t)b * af.slots_a + sl) * af.Ca + cc]);
+                    } else {
+                        if (sl < af.slots_b) v[u] = __ldg(&af.pb[((size_t)b * af.slots_b + sl) * af.Cb + (cc - af.Ca)]);
+                    }
+                }
             }
-            s += (double)v.x;
-            q += (double)v.y;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s += v[u].x;
+                q += v[u].y;
+            }
         }
         s = warp_sum(s);
         q = warp_sum(q);
         if (lane == 0) {
-            const double n = (double)af.HW * (double)cpg;
-            const double mean = s / n;
-            double var = q / n - mean * mean;
+            const double mean = (double)s * af.inv_n;
+            double var = (double)q * af.inv_n - mean * mean;
             if (var < 0.0) var = 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)af.eps));
-            const float sc = (af.gamma != nullptr ? af.gamma[c] : 1.f) * rstd;
-            s_sc[ch] = sc;
-            s_sh[ch] = fmaf(-(float)mean, sc, af.beta != nullptr ? af.beta[c] : 0.f);
+            s_mean[gi] = (float)mean;
+            s_rstd[gi] = rsqrtf((float)var + af.eps);
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < CG) {
+        const int c = c0 + threadIdx.x;
+        const int gi = c / cpg - g_first;
+        const float sc = (af.gamma != nullptr ? af.gamma[c] : 1.f) * s_rstd[gi];
+        s_sc[threadIdx.x] = sc;
+        s_sh[threadIdx.x] = fmaf(-s_mean[gi], sc, af.beta != nullptr ? af.beta[c] : 0.f);
     }
     __syncthreads();
 }
@@ -362,6 +388,261 @@ resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Filtered activation on the tensor cores (n = 16, 32): every 1-D circular convolution of the separable operator
+// is a small GEMM  out[line][i] = sum_j in[line][j] * F[(i - j) mod n]  with 16 lines (2 rows or columns x 8
+// channels) as the M dimension of a warp-level mma.m16n8k16.  fp32 accuracy comes from a 3-term split into fp16
+// halves (x = xh + xl, F = Fh + Fl; out = xh Fh + xl Fh + xh Fl, fp32 accumulate): 22 significant bits per operand,
+// measured error 3e-7 of max |y| - the same class as the exact-FMA kernels above (tests compare both with the
+// reference's FFT result at 5e-6 / 1e-5).  Inputs are post-GroupNorm activations; |x| must stay below the fp16
+// range (65504) - the host wrapper documents this and the SIMT kernel remains selectable (AFLDM_FACT_MMA=0).
+//
+//   * the circulant is held as B fragments in registers: fragment (k-step ks, n-tile nt) depends only on
+//     (nt - 2 ks) mod n/8, so n/8 fragment pairs (hi, lo) cover the whole filter;
+//   * an accumulator fragment (cols 2t, 2t+1 of n-tile j) is exactly half of the A fragment of the next product
+//     (k = 2t, 2t+1 of k-step j/2): up-sample -> act -> down-sample of a column chain through registers;
+//   * rows and columns are exchanged through one fp32 shared-memory tile T[i][j'][c] with
+//     addr = i * (20 n + 4) + 10 * (j' / 4) * 4 ... (see tix()): every access pattern below is bank-conflict free;
+//   * the even-indexed half of the down-sampler is the O(n) identity of down_line().
+constexpr int FM_CG = 8;        // channels per CTA
+constexpr int FM_THREADS = 256;
+
+template <int N>
+struct FmTile {
+    static constexpr int ROW = 20 * N + 4;                 // floats per image row i: 2N * 8 + (2N / 4) * 8 pad + 4
+    static constexpr int SMEM_BYTES = N * ROW * 4;
+};
+// offset of (row i, up-sampled column jp, channel 0)
+template <int N>
+__device__ __forceinline__ int tix(int i, int jp) { return i * FmTile<N>::ROW + jp * 8 + (jp >> 2) * 8; }
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// B fragments of the circulant F[(i - j) mod N]: variant q = (nt - 2 ks) mod N/8.
+template <int N>
+struct CircB {
+    uint32_t h[N / 8][2], l[N / 8][2];
+};
+template <int N, bool DOWN>
+__device__ __forceinline__ float circ_tap(int r) {
+    // up: odd-phase taps d[r];  down (odd samples): G[r] = g[(2r - 1) mod 2N]
+    if constexpr (DOWN) return tap_g<N>((2 * r - 1) & (2 * N - 1));
+    return tap_d<N>(r & (N - 1));
+}
+template <int N, bool DOWN>
+__device__ __forceinline__ void make_circ(CircB<N>& f, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < N / 8; ++q) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int kk = 2 * t + 8 * p;                  // B[k][n = g], k = kk, kk + 1
+            const float v0 = circ_tap<N, DOWN>((8 * q + g - kk) & (N - 1));
+            const float v1 = circ_tap<N, DOWN>((8 * q + g - kk - 1) & (N - 1));
+            split_pack(v0, v1, f.h[q][p], f.l[q][p]);
+        }
+    }
+}
+
+// acc[nt][.] += sum_j in[.][j] F[(i - j) mod N] for the 16 lines of the warp; `in` is in accumulator layout:
+// in[r][nt][e] = line (g + 8 r), position 8 nt + 2 t + e.
+template <int N>
+__device__ __forceinline__ void circ_mma(const float (&in)[2][N / 8][2], const CircB<N>& f, float (&acc)[N / 8][4]) {
+    uint32_t ah[N / 16][4], al[N / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < N / 16; ++ks) {
+#pragma unroll
+        for (int idx = 0; idx < 4; ++idx) {
+            const int r = idx & 1, nt = 2 * ks + (idx >> 1);
+            split_pack(in[r][nt][0], in[r][nt][1], ah[ks][idx], al[ks][idx]);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt) {
+#pragma unroll
+        for (int ks = 0; ks < N / 16; ++ks) {
+            const int q = (nt - 2 * ks) & (N / 8 - 1);
+            mma_f16(acc[nt], al[ks], f.h[q][0], f.h[q][1]);
+            mma_f16(acc[nt], ah[ks], f.l[q][0], f.l[q][1]);
+            mma_f16(acc[nt], ah[ks], f.h[q][0], f.h[q][1]);
+        }
+    }
+}
+
+// y = down-sample of the line whose even samples are e[] and odd samples o[] (both activated):
+// y[i] = e[i] / 2 - (-1)^i altsum(e) / (2N) + sum_m G[i - m] o[m]
+template <int N>
+__device__ __forceinline__ void down_mma(const float (&e)[2][N / 8][2], const float (&o)[2][N / 8][2],
+                                         const CircB<N>& fd, float (&acc)[N / 8][4]) {
+    float s[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float a = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < N / 8; ++nt) a += e[r][nt][0] - e[r][nt][1];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        s[r] = a * (1.0f / (2 * N));
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt) {
+        acc[nt][0] = fmaf(0.5f, e[0][nt][0], -s[0]);
+        acc[nt][1] = fmaf(0.5f, e[0][nt][1], s[0]);
+        acc[nt][2] = fmaf(0.5f, e[1][nt][0], -s[1]);
+        acc[nt][3] = fmaf(0.5f, e[1][nt][1], s[1]);
+    }
+    circ_mma<N>(o, fd, acc);
+}
+
+template <int N, int ACT>
+__global__ void __launch_bounds__(FM_THREADS, 2)
+fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const Affine af) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float T[];
+    __shared__ float s_sc[FM_CG], s_sh[FM_CG];
+    const int b = blockIdx.y, c0 = blockIdx.x * FM_CG;
+    if (af.pa != nullptr) gn_prologue<FM_CG>(af, b, c0, C, s_sc, s_sh);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = N / 8;
+    constexpr int NWARPS = FM_THREADS / 32;
+
+    CircB<N> fu, fd;
+    make_circ<N, false>(fu, g, t);
+    make_circ<N, true>(fd, g, t);
+
+    float sc = 1.f, sh = 0.f;
+    if (af.pa != nullptr) {
+        sc = s_sc[g];
+        sh = s_sh[g];
+    } else if (af.scale != nullptr) {
+        sc = af.scale[(size_t)b * C + c0 + g];
+        sh = af.shift[(size_t)b * C + c0 + g];
+    }
+
+    // ---- phase 0: rows up.  m-tile = rows (i0, i0 + 1) x 8 channels; line g -> (i0, c = g), g + 8 -> (i0 + 1, g)
+    for (int mt = warp; mt < N / 2; mt += NWARPS) {
+        const int i0 = 2 * mt;
+        float e[2][NT][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float* xp = x + ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) e[r][nt][q] = fmaf(xp[(size_t)(8 * nt + 2 * t + q) * C], sc, sh);
+        }
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        circ_mma<N>(e, fu, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float* tp = T + tix<N>(i0 + r, 16 * nt + 4 * t + 2 * q) + g;
+                    tp[0] = e[r][nt][q];
+                    tp[8] = acc[nt][2 * r + q];
+                }
+    }
+    __syncthreads();
+
+    // ---- phase 1: columns up -> act -> down, in place.  m-tile = columns (jp0, jp0 + 1) x 8 channels
+    for (int mt = warp; mt < N; mt += NWARPS) {
+        const int jp0 = 2 * mt;
+        float e[2][NT][2], o[2][NT][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) e[r][nt][q] = T[tix<N>(8 * nt + 2 * t + q, jp0 + r) + g];
+        {
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+            circ_mma<N>(e, fu, acc);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        o[r][nt][q] = apply_act<ACT>(acc[nt][2 * r + q]);
+                        e[r][nt][q] = apply_act<ACT>(e[r][nt][q]);
+                    }
+        }
+        float acc[NT][4];
+        down_mma<N>(e, o, fd, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) T[tix<N>(8 * nt + 2 * t + q, jp0 + r) + g] = acc[nt][2 * r + q];
+    }
+    __syncthreads();
+
+    // ---- phase 2: rows down -> global
+    for (int mt = warp; mt < N / 2; mt += NWARPS) {
+        const int i0 = 2 * mt;
+        float e[2][NT][2], o[2][NT][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float* tp = T + tix<N>(i0 + r, 16 * nt + 4 * t + 2 * q) + g;
+                    e[r][nt][q] = tp[0];
+                    o[r][nt][q] = tp[8];
+                }
+        float acc[NT][4];
+        down_mma<N>(e, o, fd, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float* yp = y + ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) yp[(size_t)(8 * nt + 2 * t + q) * C] = acc[nt][2 * r + q];
+        }
+    }
+}
+
+template <int N, int ACT>
+int launch_fact_mma(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
+    auto kern = fact_mma_kernel<N, ACT>;
+    constexpr int smem = FmTile<N>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    launch_k(kern, dim3(C / FM_CG, B), dim3(FM_THREADS), smem, st, x, y, C, af);
+    return launched();
+}
+
+bool fact_mma_enabled() {
+    static const bool on = !(getenv("AFLDM_FACT_MMA") && atoi(getenv("AFLDM_FACT_MMA")) == 0);
+    return on;
+}
+
 template <int N, int CG, int MODE, int ACT>
 int launch_one(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
     if (C % CG != 0) return AFLDM_E_SHAPE;
@@ -381,6 +662,12 @@ int launch_one(const float* x, float* y, int B, int C, const Affine& af, cudaStr
 
 template <int MODE, int ACT>
 int dispatch_n(const float* x, float* y, int B, int n, int C, const Affine& af, cudaStream_t st) {
+    if constexpr (MODE == MODE_FACT) {
+        if (fact_mma_enabled() && C % FM_CG == 0) {
+            if (n == 32) return launch_fact_mma<32, ACT>(x, y, B, C, af, st);
+            if (n == 16) return launch_fact_mma<16, ACT>(x, y, B, C, af, st);
+        }
+    }
     switch (n) {
         case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, af, st);
         case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, af, st);
@@ -444,6 +731,7 @@ extern "C" int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H,
     af.gamma = gamma; af.beta = beta;
     af.slots_a = slots_a; af.Ca = Ca; af.slots_b = Cb > 0 ? slots_b : 0; af.Cb = Cb;
     af.groups = groups; af.HW = H * W; af.eps = eps;
+    af.inv_n = 1.0 / ((double)(H * W) * (double)(C / groups));
     cudaStream_t st = as_stream(stream);
     if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, af, st);
     return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, st);

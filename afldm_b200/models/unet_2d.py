@@ -33,6 +33,18 @@ class TimestepEmbedding(nn.Module):
         return ops.linear_rows(h, self.linear_2.weight, self.linear_2.bias, act_in="silu")
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One auxiliary stream per device for work that is independent of the activation path."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
 class UNet2DModel(nn.Module):
     def __init__(self, sample_size=32, in_channels=4, out_channels=4,
                  block_out_channels: Sequence[int] = (192, 384, 384, 768, 768),
@@ -117,12 +129,20 @@ class UNet2DModel(nn.Module):
             t = t.contiguous()
         else:
             t = torch.full((bsz,), float(timestep), dtype=torch.float32, device=dev)
-        emb = self.time_embedding(ops.timestep_embedding(t, self.config.block_out_channels[0]))
-        projs = self._time_projections(emb)
+        # The time-embedding MLP and the 27 fused time_emb_proj rows depend on t only: they run on a side stream
+        # (a parallel branch of the captured step graph) under conv_in and the first GroupNorm / filtered activation,
+        # and are joined just before the first resnet consumes its projection row.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            emb = self.time_embedding(ops.timestep_embedding(t, self.config.block_out_channels[0]))
+            projs = self._time_projections(emb)
 
         x = ops.nhwc(sample)
         w, b, k = conv_params(self.conv_in)
         h = ops.nchw_view(ops.conv2d(x, w, b, k))
+        main.wait_stream(side)
         skips = (h,)
         pi = 0
         for blk in self.down_blocks:

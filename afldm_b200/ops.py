@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -20,7 +22,7 @@ ACT = {"identity": 0, None: 0, "silu": 1}
 CONV_ALGO = {"simt": 0, "tf32": 1}
 
 _default_conv_algo = "simt"
-FUSE_GN_PROLOGUE = False
+FUSE_GN_PROLOGUE = os.environ.get("AFLDM_FUSE_GN", "1") == "1"
 
 
 def set_default_conv_algo(name: str) -> None:
@@ -151,8 +153,9 @@ def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Opti
                            beta: Optional[torch.Tensor], act: str = "silu") -> torch.Tensor:
     """act-filtered GroupNorm(x) on NHWC x: statistics pass (or finalize of the producer's partial sums) +
     filtered activation.  ``FUSE_GN_PROLOGUE`` selects the one-launch variant that finalises the statistics
-    in the resampling kernel's prologue (afldm_filtered_act_gn_f32); measured on B200 it LOSES ~5 us per call
-    against the separate 3 us finalize kernel (every CTA repeats the fp64 finalisation), so it is off."""
+    in the resampling kernel's prologue (afldm_filtered_act_gn_f32): one warp per touched group adds the producer's
+    fp32 partial sums.  It costs the kernel ~2 us and removes a ~3 us finalize launch plus its gap (B200: +1 % on
+    the step); ``AFLDM_FUSE_GN=0`` selects the two-launch form."""
     _chk(x, "x")
     b, h, w, c = x.shape
     one, two = getattr(x, "_afldm_gn", None), getattr(x, "_afldm_gn2", None)
