@@ -12,6 +12,9 @@
 // scale * log2 e); the running max is updated once per 8 keys.
 #include <math.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace afldm {
@@ -156,7 +159,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -173,7 +176,7 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, one MUFU; -i
 // 1 for short ones (more CTAs).  K fragments are read as 64-bit words: MMA k-index t <- head-dim column 2t,
 // t + 4 <- 2t + 1 inside each 8-column chunk, the Q fragment uses the same permutation.
 template <int D, int MT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MT == 2 ? 3 : 5)
 attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
                      const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                      int Bkv_rep, int Nq, int Nk, float qscale) {
@@ -263,77 +266,86 @@ attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __re
         const float* Kt = Kbuf(buf);
         const float* Vt = Vbuf(buf);
 
-        // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
-        float s[MT][8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
-            const float* kr = &Kt[(nt * 8 + g) * PK + 2 * t];
-#pragma unroll
-            for (int ks = 0; ks < DK; ++ks) {
-                const float2 kb = *reinterpret_cast<const float2*>(kr + 8 * ks);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) mma_tf32(s[mt][nt], qa[mt][ks], __float_as_uint(kb.x), __float_as_uint(kb.y));
-            }
-        }
-        if (nk < KT) {                  // only the last tile of a ragged sequence has keys to mask
-#pragma unroll
+        // The tile body exists twice: the hot copy for full tiles carries no masking code at all (as one body the
+        // compiler if-converts the tail mask into 64 always-executed selects per 32 x 64 scores).
+        auto tile_body = [&](auto masked) {
+            // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+            float s[MT][8][4];
+    #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const int key = nt * 8 + 2 * t;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    if (key >= nk) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
-                    if (key + 1 >= nk) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+    #pragma unroll
+                for (int mt = 0; mt < MT; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+                const float* kr = &Kt[(nt * 8 + g) * PK + 2 * t];
+    #pragma unroll
+                for (int ks = 0; ks < DK; ++ks) {
+                    const float2 kb = *reinterpret_cast<const float2*>(kr + 8 * ks);
+    #pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) mma_tf32(s[mt][nt], qa[mt][ks], __float_as_uint(kb.x), __float_as_uint(kb.y));
                 }
             }
-        }
-        float nm[MT][2];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+            if constexpr (decltype(masked)::value) {    // only the last tile of a ragged sequence has keys to mask
+    #pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int key = nt * 8 + 2 * t;
+    #pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (key >= nk) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
+                        if (key + 1 >= nk) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+                    }
+                }
             }
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float n0 = fmaxf(mrun[mt][0], mx0), n1 = fmaxf(mrun[mt][1], mx1);   // finite: key k0 is always valid
-            const float c0 = ex2_approx(mrun[mt][0] - n0), c1 = ex2_approx(mrun[mt][1] - n1);
-            mrun[mt][0] = n0; mrun[mt][1] = n1;
-            nm[mt][0] = n0; nm[mt][1] = n1;
-            lrun[mt][0] *= c0; lrun[mt][1] *= c1;
-#pragma unroll
-            for (int dn = 0; dn < DK; ++dn) {
-                oacc[mt][dn][0] *= c0; oacc[mt][dn][1] *= c0;
-                oacc[mt][dn][2] *= c1; oacc[mt][dn][3] *= c1;
-            }
-        }
-        // P = exp2(S - m); O += P V
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            uint32_t pa[MT][4];
-#pragma unroll
+            float nm[MT][2];
+    #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const float p00 = ex2_approx(s[mt][nt][0] - nm[mt][0]), p01 = ex2_approx(s[mt][nt][1] - nm[mt][0]);
-                const float p10 = ex2_approx(s[mt][nt][2] - nm[mt][1]), p11 = ex2_approx(s[mt][nt][3] - nm[mt][1]);
-                lrun[mt][0] += p00 + p01;
-                lrun[mt][1] += p10 + p11;
-                // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
-                pa[mt][0] = to_tf32(p00); pa[mt][1] = to_tf32(p10); pa[mt][2] = to_tf32(p01); pa[mt][3] = to_tf32(p11);
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+    #pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                const float n0 = fmaxf(mrun[mt][0], mx0), n1 = fmaxf(mrun[mt][1], mx1);   // finite: key k0 is always valid
+                const float c0 = ex2_approx(mrun[mt][0] - n0), c1 = ex2_approx(mrun[mt][1] - n1);
+                mrun[mt][0] = n0; mrun[mt][1] = n1;
+                nm[mt][0] = n0; nm[mt][1] = n1;
+                lrun[mt][0] *= c0; lrun[mt][1] *= c1;
+    #pragma unroll
+                for (int dn = 0; dn < DK; ++dn) {
+                    oacc[mt][dn][0] *= c0; oacc[mt][dn][1] *= c0;
+                    oacc[mt][dn][2] *= c1; oacc[mt][dn][3] *= c1;
+                }
             }
-            const float* vr0 = &Vt[(nt * 8 + 2 * t) * P + g];
-            const float* vr1 = vr0 + P;
-#pragma unroll
-            for (int dn = 0; dn < DK; ++dn) {
-                const uint32_t b0 = __float_as_uint(vr0[8 * dn]), b1 = __float_as_uint(vr1[8 * dn]);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) mma_tf32(oacc[mt][dn], pa[mt], b0, b1);
+            // P = exp2(S - m); O += P V
+    #pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                uint32_t pa[MT][4];
+    #pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const float p00 = ex2_approx(s[mt][nt][0] - nm[mt][0]), p01 = ex2_approx(s[mt][nt][1] - nm[mt][0]);
+                    const float p10 = ex2_approx(s[mt][nt][2] - nm[mt][1]), p11 = ex2_approx(s[mt][nt][3] - nm[mt][1]);
+                    lrun[mt][0] += p00 + p01;
+                    lrun[mt][1] += p10 + p11;
+                    // A fragment: k = t <- key 2t (c0 / c2), k = t + 4 <- key 2t + 1 (c1 / c3)
+                    // p in [0, 1]: round-to-nearest TF32 is one integer add of half an ulp of the 10-bit mantissa (the MMA
+                    // ignores the low 13 bits); cvt.rna.tf32 costs three instructions with its NaN / range handling
+                    pa[mt][0] = __float_as_uint(p00) + 0x1000u; pa[mt][1] = __float_as_uint(p10) + 0x1000u;
+                    pa[mt][2] = __float_as_uint(p01) + 0x1000u; pa[mt][3] = __float_as_uint(p11) + 0x1000u;
+                }
+                const float* vr0 = &Vt[(nt * 8 + 2 * t) * P + g];
+                const float* vr1 = vr0 + P;
+    #pragma unroll
+                for (int dn = 0; dn < DK; ++dn) {
+                    const uint32_t b0 = __float_as_uint(vr0[8 * dn]), b1 = __float_as_uint(vr1[8 * dn]);
+    #pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) mma_tf32(oacc[mt][dn], pa[mt], b0, b1);
+                }
             }
-        }
+        };
+        if (nk < KT) tile_body(std::true_type{});
+        else tile_body(std::false_type{});
         __syncthreads();                                       // everyone is done with `buf` before it is refilled
     }
 #pragma unroll
@@ -381,7 +393,9 @@ template <int D>
 int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
                int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
     // two query tiles per warp once there are enough CTAs left to fill the chip twice over
-    if (D <= 32 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
+    static const int force_mt = getenv("AFLDM_ATTN_MT") ? atoi(getenv("AFLDM_ATTN_MT")) : 0;
+    if (force_mt == 1) return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    if (D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
         return launch_mma_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
     return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
 }

@@ -56,7 +56,14 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 // (1 ulp): ~6 instructions instead of ~22 for expf + IEEE division, which matters because the filtered
 // activation applies it 64 times per thread inside an instruction-cache-bound unrolled kernel.  Measured
 // parity vs the reference's exact SiLU stays within the 1e-5 op tolerance (tests/test_gpu_ops.py).
-__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+// Written as ex2.approx / rcp.approx directly: __fdividef adds a range-scaling sequence (FSETP + 2 FMUL) that
+// 1 + e^-z in [1, inf] never needs; z * rcp(inf) = -0 is the correct limit for very negative finite z.
+__device__ __forceinline__ float silu_f(float z) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return z * r;
+}
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float z) {

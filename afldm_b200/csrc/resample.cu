@@ -417,7 +417,7 @@ template <int N>
 __device__ __forceinline__ int tix(int i, int jp) { return i * FmTile<N>::ROW + jp * 8 + (jp >> 2) * 8; }
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -468,14 +468,18 @@ __device__ __forceinline__ void circ_mma(const float (&in)[2][N / 8][2], const C
             split_pack(in[r][nt][0], in[r][nt][1], ah[ks][idx], al[ks][idx]);
         }
     }
+    // consecutive MMAs go to different accumulators (N/8 independent chains); small terms first
 #pragma unroll
-    for (int nt = 0; nt < N / 8; ++nt) {
+    for (int term = 0; term < 3; ++term) {
 #pragma unroll
         for (int ks = 0; ks < N / 16; ++ks) {
-            const int q = (nt - 2 * ks) & (N / 8 - 1);
-            mma_f16(acc[nt], al[ks], f.h[q][0], f.h[q][1]);
-            mma_f16(acc[nt], ah[ks], f.l[q][0], f.l[q][1]);
-            mma_f16(acc[nt], ah[ks], f.h[q][0], f.h[q][1]);
+#pragma unroll
+            for (int nt = 0; nt < N / 8; ++nt) {
+                const int q = (nt - 2 * ks) & (N / 8 - 1);
+                if (term == 0) mma_f16(acc[nt], al[ks], f.h[q][0], f.h[q][1]);
+                else if (term == 1) mma_f16(acc[nt], ah[ks], f.l[q][0], f.l[q][1]);
+                else mma_f16(acc[nt], ah[ks], f.h[q][0], f.h[q][1]);
+            }
         }
     }
 }
@@ -532,18 +536,36 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
         sh = af.shift[(size_t)b * C + c0 + g];
     }
 
+    // ---- stage: x[b][:, :, c0 .. c0 + 8) -> the even columns of T, 2 x 16 B per pixel with cp.async, all in
+    // flight at once (one thread per half pixel), so that no MMA chain below waits on a global load.
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        for (int idx = threadIdx.x; idx < N * N * 2; idx += FM_THREADS) {
+            const int half = idx & 1, pix = idx >> 1, i = pix / N, j = pix - i * N;
+            const float* src = x + ((size_t)(b * N + i) * N + j) * C + c0 + 4 * half;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(T + tix<N>(i, 2 * j) + 4 * half);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int idx = threadIdx.x; idx < N * N * FM_CG; idx += FM_THREADS) {
+            const int c = idx & 7, pix = idx >> 3, i = pix / N, j = pix - i * N;
+            T[tix<N>(i, 2 * j) + c] = x[((size_t)(b * N + i) * N + j) * C + c0 + c];
+        }
+    }
+    __syncthreads();
+
     // ---- phase 0: rows up.  m-tile = rows (i0, i0 + 1) x 8 channels; line g -> (i0, c = g), g + 8 -> (i0 + 1, g)
     for (int mt = warp; mt < N / 2; mt += NWARPS) {
         const int i0 = 2 * mt;
         float e[2][NT][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const float* xp = x + ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) e[r][nt][q] = fmaf(xp[(size_t)(8 * nt + 2 * t + q) * C], sc, sh);
-        }
+                for (int q = 0; q < 2; ++q)
+                    e[r][nt][q] = fmaf(T[tix<N>(i0 + r, 16 * nt + 4 * t + 2 * q) + g], sc, sh);
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
