@@ -39,6 +39,8 @@ SIGNATURES = {
     "afldm_groupnorm_finalize_f32": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "afldm_linear_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "afldm_attention_f32": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "afldm_attention_f16": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "afldm_conv2d_f16out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_softmax_rows_f32": (_i, [_p, _ll, _i, _i, _f, _p]),
     "afldm_timestep_embedding_f32": (_i, [_p, _p, _i, _i, _p]),
     "afldm_concat_channels_f32": (_i, [_p, _i, _p, _i, _p, _ll, _p]),

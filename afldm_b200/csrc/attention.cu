@@ -10,6 +10,7 @@
 // broadcasts (all threads of a CTA walk the keys in lock-step), so shared-memory traffic is
 // one 128-bit broadcast per 4 FMAs.  Scores are kept in the exp2 domain (q is pre-multiplied by
 // scale * log2 e); the running max is updated once per 8 keys.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <cstdlib>
@@ -400,6 +401,278 @@ int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int 
     return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// fp16-operand variant (afldm_attention_f16): q, k, v arrive as fp16 (the QKV projection's epilogue stores them
+// that way), products run on mma.m16n8k16 with fp32 accumulation, softmax in fp32.  fp16 carries the same 11
+// significant bits as the TF32 operands of the kernel above (narrower exponent: |q|, |k|, |v| < 65504), so this
+// is the same numeric class at half the operand bytes and half the tensor-pipe time, and - what matters, the
+// TF32 kernel is issue-bound (~750 instructions per 96 HMMA) - far fewer instructions: K and V fragments come
+// from ldmatrix (.trans for V) instead of scalar LDS, P is packed two scores per F2FP, the softmax scale is
+// folded into the exponent FFMA.
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t addr, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// D: head dim (multiple of 8, <= 64); MT: 16-row query tiles per warp.  4 warps, 64 * MT queries per CTA.
+template <int D, int MT>
+__global__ void __launch_bounds__(128, MT == 2 ? 3 : 5)
+attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __restrict__ k,
+                     const __half* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
+                     int Bkv_rep, int Nq, int Nk, float scale_log2e) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int KT = 64;                       // keys per tile
+    constexpr int DP = (D + 15) / 16 * 16;       // head dim padded to the MMA k (zero columns)
+    constexpr int KS = DP / 16;                  // k-steps of Q.K^T
+    constexpr int DN = D / 8;                    // n-tiles of P.V
+    constexpr int PH = DP + 8;                   // smem row pitch in halves: rows 16 B apart mod 128 B -> conflict-free ldmatrix
+    constexpr int CH = D / 8;                    // 16-byte chunks per row
+    extern __shared__ __align__(16) __half att_h[];             // [K0 | K1 | V0 | V1], each KT * PH halves
+    auto Kbuf = [&](int i) { return att_h + i * (KT * PH); };
+    auto Vbuf = [&](int i) { return att_h + (2 + i) * (KT * PH); };
+    const int b = blockIdx.z, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int bkv = b / Bkv_rep;
+    const int wrow = blockIdx.x * (64 * MT) + warp * (16 * MT);
+
+    // zero the pad columns [D, PH) of all four buffers once (cp.async only ever writes columns < D)
+    for (int idx = threadIdx.x; idx < 4 * KT * (PH - D) / 8; idx += blockDim.x) {
+        const int row = idx / ((PH - D) / 8), c8 = idx - row * ((PH - D) / 8);
+        *reinterpret_cast<uint4*>(att_h + row * PH + D + 8 * c8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    const __half* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    const __half* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;
+    auto load_tile = [&](int buf, int k0) {
+        const int nk = min(KT, Nk - k0);
+        __half* kb = Kbuf(buf);
+        __half* vb = Vbuf(buf);
+#pragma unroll
+        for (int it = 0; it < (KT * CH + 127) / 128; ++it) {
+            const int idx = it * 128 + threadIdx.x;
+            if (idx >= KT * CH) break;
+            const int key = idx / CH, c8 = idx - key * CH;
+            __half* kd = kb + key * PH + 8 * c8;
+            __half* vd = vb + key * PH + 8 * c8;
+            if (key < nk) {
+                const uint32_t ks_ = (uint32_t)__cvta_generic_to_shared(kd), vs_ = (uint32_t)__cvta_generic_to_shared(vd);
+                const size_t goff = (size_t)(k0 + key) * kv_pitch + 8 * c8;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_), "l"(kbase + goff) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_), "l"(vbase + goff) : "memory");
+            } else {
+                *reinterpret_cast<uint4*>(kd) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(vd) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_tile(0, 0);
+
+    // Q fragments: a0 = (row g, k 2t..2t+1), a1 = (row g+8, same), a2 / a3 = k + 8; columns >= D are zero
+    uint32_t qa[MT][KS][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = wrow + mt * 16 + g, r1 = r0 + 8;
+        const __half* q0 = q + ((size_t)b * Nq + min(r0, Nq - 1)) * q_pitch + head * D;
+        const __half* q1 = q + ((size_t)b * Nq + min(r1, Nq - 1)) * q_pitch + head * D;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int ca = 16 * ks + 2 * t, cb = ca + 8;
+            qa[mt][ks][0] = ca < D ? *reinterpret_cast<const uint32_t*>(q0 + ca) : 0u;
+            qa[mt][ks][1] = ca < D ? *reinterpret_cast<const uint32_t*>(q1 + ca) : 0u;
+            qa[mt][ks][2] = cb < D ? *reinterpret_cast<const uint32_t*>(q0 + cb) : 0u;
+            qa[mt][ks][3] = cb < D ? *reinterpret_cast<const uint32_t*>(q1 + cb) : 0u;
+        }
+    }
+    float oacc[MT][DN][4];
+    float mrun[MT][2], lrun[MT][2];      // running max of the RAW scores, running sum of exp2((s - m) * scale_log2e)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int i = 0; i < DN; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oacc[mt][i][j] = 0.f;
+        mrun[mt][0] = mrun[mt][1] = -INFINITY;
+        lrun[mt][0] = lrun[mt][1] = 0.f;
+    }
+    // ldmatrix lane roles: matrix m = lane / 8, row r = lane % 8
+    const int lm = lane >> 3, lr = lane & 7;
+
+    int buf = 0;
+    for (int k0 = 0; k0 < Nk; k0 += KT, buf ^= 1) {
+        const int nk = min(KT, Nk - k0);
+        if (k0 + KT < Nk) {
+            load_tile(buf ^ 1, k0 + KT);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint32_t Kt = (uint32_t)__cvta_generic_to_shared(Kbuf(buf));
+        const uint32_t Vt = (uint32_t)__cvta_generic_to_shared(Vbuf(buf));
+
+        auto tile_body = [&](auto masked) {
+            // S = Q K^T: B fragment of (n-tile nt, k-step ks) = two 8x8 matrices: keys nt*8.., columns 16 ks + {0, 8}
+            float s[MT][8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+                if constexpr (KS % 2 == 0) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks += 2) {
+                        uint32_t kb[4];
+                        ldsm_x4(Kt + (uint32_t)(((nt * 8 + lr) * PH + 16 * ks + 8 * lm) * 2), kb);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            mma_f16_16816(s[mt][nt], qa[mt][ks], kb[0], kb[1]);
+                            mma_f16_16816(s[mt][nt], qa[mt][ks + 1], kb[2], kb[3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        uint32_t kb[2];
+                        ldsm_x2(Kt + (uint32_t)(((nt * 8 + lr) * PH + 16 * ks + 8 * (lm & 1)) * 2), kb);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) mma_f16_16816(s[mt][nt], qa[mt][ks], kb[0], kb[1]);
+                    }
+                }
+            }
+            if constexpr (decltype(masked)::value) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int key = nt * 8 + 2 * t;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (key >= nk) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
+                        if (key + 1 >= nk) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+                    }
+                }
+            }
+            float nms[MT][2];          // new max * scale_log2e
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                const float n0 = fmaxf(mrun[mt][0], mx0), n1 = fmaxf(mrun[mt][1], mx1);   // finite: key k0 is valid
+                const float c0 = ex2_approx((mrun[mt][0] - n0) * scale_log2e), c1 = ex2_approx((mrun[mt][1] - n1) * scale_log2e);
+                mrun[mt][0] = n0; mrun[mt][1] = n1;
+                nms[mt][0] = n0 * scale_log2e; nms[mt][1] = n1 * scale_log2e;
+                lrun[mt][0] *= c0; lrun[mt][1] *= c1;
+#pragma unroll
+                for (int dn = 0; dn < DN; ++dn) {
+                    oacc[mt][dn][0] *= c0; oacc[mt][dn][1] *= c0;
+                    oacc[mt][dn][2] *= c1; oacc[mt][dn][3] *= c1;
+                }
+            }
+            // P = exp2(s * scale_log2e - m * scale_log2e); O += P V, 16 keys (two n-tiles of S) per k-step
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t pa[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int nt = 2 * kk + hh;
+                        const float p00 = ex2_approx(fmaf(s[mt][nt][0], scale_log2e, -nms[mt][0]));
+                        const float p01 = ex2_approx(fmaf(s[mt][nt][1], scale_log2e, -nms[mt][0]));
+                        const float p10 = ex2_approx(fmaf(s[mt][nt][2], scale_log2e, -nms[mt][1]));
+                        const float p11 = ex2_approx(fmaf(s[mt][nt][3], scale_log2e, -nms[mt][1]));
+                        lrun[mt][0] += p00 + p01;
+                        lrun[mt][1] += p10 + p11;
+                        pa[mt][2 * hh] = pack_h2(p00, p01);          // row g
+                        pa[mt][2 * hh + 1] = pack_h2(p10, p11);      // row g + 8
+                    }
+                }
+                // V fragment of (k-step kk, n-tile dn): transposed 8x8 matrices, keys 16 kk + {0, 8}, columns 8 dn
+#pragma unroll
+                for (int dn = 0; dn < DN; ++dn) {
+                    uint32_t vb[2];
+                    ldsm_x2_trans(Vt + (uint32_t)(((16 * kk + 8 * (lm & 1) + lr) * PH + 8 * dn) * 2), vb);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) mma_f16_16816(oacc[mt][dn], pa[mt], vb[0], vb[1]);
+                }
+            }
+        };
+        if (nk < KT) tile_body(std::true_type{});
+        else tile_body(std::false_type{});
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        float l0 = lrun[mt][0], l1 = lrun[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = wrow + mt * 16 + g, r1 = r0 + 8;
+        if (r0 < Nq) {
+            float* op = o + ((size_t)b * Nq + r0) * o_pitch + head * D + 2 * t;
+#pragma unroll
+            for (int dn = 0; dn < DN; ++dn)
+                *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[mt][dn][0] * i0, oacc[mt][dn][1] * i0);
+        }
+        if (r1 < Nq) {
+            float* op = o + ((size_t)b * Nq + r1) * o_pitch + head * D + 2 * t;
+#pragma unroll
+            for (int dn = 0; dn < DN; ++dn)
+                *reinterpret_cast<float2*>(op + 8 * dn) = make_float2(oacc[mt][dn][2] * i1, oacc[mt][dn][3] * i1);
+        }
+    }
+}
+
+template <int D, int MT>
+int launch_f16_mt(const __half* q, int q_pitch, const __half* k, const __half* v, int kv_pitch, float* o, int o_pitch,
+                  int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+    const float scale_log2e = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
+    constexpr int DP = (D + 15) / 16 * 16;
+    constexpr int smem = 4 * 64 * (DP + 8) * 2;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    configured = true;
+    launch_k(attention_f16_kernel<D, MT>, dim3(ceil_div(Nq, 64 * MT), heads, B), dim3(128), smem, st,
+        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, scale_log2e);
+    return launched();
+}
+
+template <int D>
+int launch_f16(const __half* q, int q_pitch, const __half* k, const __half* v, int kv_pitch, float* o, int o_pitch,
+               int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+    if (D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
+        return launch_f16_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    return launch_f16_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+}
+
 template <int D>
 int launch(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch, float* o, int o_pitch,
            int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
@@ -464,4 +737,32 @@ extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, 
         default: return AFLDM_E_NOKERNEL;
     }
 #undef AFLDM_ATT_CASE
+}
+
+extern "C" int afldm_attention_f16(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch, float* o,
+                                   int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                                   afldm_stream_t stream) {
+    if (q == nullptr || k == nullptr || v == nullptr || o == nullptr) return AFLDM_E_ARG;
+    if (B <= 0 || Bkv <= 0 || Nq <= 0 || Nk <= 0 || heads <= 0 || d <= 0) return AFLDM_E_ARG;
+    if (B % Bkv != 0) return AFLDM_E_SHAPE;
+    if (d % 8 != 0 || q_pitch % 8 != 0 || kv_pitch % 8 != 0 || o_pitch % 2 != 0) return AFLDM_E_SHAPE;
+    if (q_pitch < heads * d || kv_pitch < heads * d || o_pitch < heads * d) return AFLDM_E_ARG;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (reinterpret_cast<uintptr_t>(o) & 7u) != 0) return AFLDM_E_ARG;
+    cudaStream_t st = as_stream(stream);
+    const __half* qh = static_cast<const __half*>(q);
+    const __half* kh = static_cast<const __half*>(k);
+    const __half* vh = static_cast<const __half*>(v);
+#define AFLDM_ATT_F16(D) \
+    case D: return launch_f16<D>(qh, q_pitch, kh, vh, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    switch (d) {
+        AFLDM_ATT_F16(8)
+        AFLDM_ATT_F16(16)
+        AFLDM_ATT_F16(24)
+        AFLDM_ATT_F16(32)
+        AFLDM_ATT_F16(40)
+        AFLDM_ATT_F16(48)
+        AFLDM_ATT_F16(64)
+        default: return AFLDM_E_NOKERNEL;
+    }
+#undef AFLDM_ATT_F16
 }

@@ -54,3 +54,12 @@ extern "C" int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, con
                               Cout, ksize, workspace, workspace_floats, gn_partial, st);
     return AFLDM_E_ARG;
 }
+
+extern "C" int afldm_conv2d_f16out(const float* x, int x_pitch, const float* w, const float* bias, void* y, int y_pitch,
+                                   int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream) {
+    if (conv_bad_args(x, x_pitch, w, static_cast<const float*>(y), y_pitch, nullptr, 0, nullptr, 0, B, H, W, Cin, Cout,
+                      ksize))
+        return AFLDM_E_ARG;
+    return conv_tc_launch(x, x_pitch, w, bias, nullptr, 0, nullptr, 0, static_cast<float*>(y), y_pitch, B, H, W, Cin, Cout,
+                          ksize, nullptr, 0, nullptr, as_stream(stream), 1);
+}

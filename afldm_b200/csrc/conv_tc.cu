@@ -20,6 +20,7 @@
 // Numeric class: TF32 (10-bit mantissa) products, fp32 accumulation - the same class as the
 // reference's default cuDNN path (torch.backends.cudnn.allow_tf32 = True).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -185,6 +186,7 @@ struct TcArgs {
     int nacc;                       // TMEM accumulator buffers (2: epilogue of item i overlaps main loop of i+1)
     int alias_staging;              // one item per CTA: the epilogue staging reuses the (then idle) stage ring
     int halo;                       // 3x3 halo mode: one A box {32 ch, BW, BH + 2} per (kw, channel chunk) serves the 3 kh taps
+    int y_half;                     // y is fp16 (y_pitch in halves): QKV projections feeding afldm_attention_f16
 };
 
 // One lane of a converged warp (elect.sync); the same lane every time for the full mask.
@@ -495,7 +497,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
                             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
                         }
-                        *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
+                        if (a.y_half) {
+                            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.y) + (size_t)mm * a.y_pitch + n) = pk;
+                        } else {
+                            *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
+                        }
                         gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
                         gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
                         gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
@@ -740,8 +750,11 @@ bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, si
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H,
                    int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
-                   cudaStream_t st) {
+                   cudaStream_t st, int y_half) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    if (y_half && (!p.ok || p.splitk > 1 || residual != nullptr || gn_partial != nullptr || (Cout & 3) != 0 ||
+                   (y_pitch & 3) != 0 || (reinterpret_cast<uintptr_t>(y) & 7u) != 0))
+        return AFLDM_E_NOKERNEL;             // fp16 stores live in the vectorised un-split epilogue only
     const int gn_slots = gn_partial != nullptr ? conv_tc_gn_slots(B, H, W, Cin, Cout, ks) : 0;
     if (gn_partial != nullptr && gn_slots == 0) return AFLDM_E_SHAPE;
     if (!p.ok || (x_pitch & 3) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
@@ -796,7 +809,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
     a.gn_partial = (p.splitk > 1) ? nullptr : gn_partial;
     a.gn_slots = gn_slots;
-    a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && aligned16(y) && (bias == nullptr || aligned16(bias)) &&
+    a.y_half = y_half;
+    a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && (y_half || aligned16(y)) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
     a.mtiles = p.mtiles; a.ntiles = p.ntiles; a.splitk = p.splitk; a.nacc = p.nacc;

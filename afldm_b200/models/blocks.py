@@ -86,9 +86,16 @@ class AttnProcessor2_0:
             gn = attn.group_norm
             scale, shift = ops.groupnorm_affine(x, gn.num_groups, gn.eps, gn.weight, gn.bias)
             xn = ops.affine_act(x, scale, shift, act="identity")
+        d = c // attn.heads
+        # TF32 class: the projections may hand q | k | v over as fp16 (same 11-bit significands as TF32 operands)
+        # to the ldmatrix / mma.m16n8k16 attention kernel
+        f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and d <= 64 and d % 8 == 0
         if encoder_hidden_states is None:
             wqkv, bqkv = fused_linear_params(attn, "qkv", (attn.to_q, attn.to_k, attn.to_v))
-            qkv = ops.conv2d(xn, wqkv, bqkv, 1).view(b, h * w, 3 * c)
+            qkv = ops.conv2d_f16out(xn, wqkv, bqkv, 1) if f16 else None
+            if qkv is None:
+                qkv = ops.conv2d(xn, wqkv, bqkv, 1)
+            qkv = qkv.view(b, h * w, 3 * c)
             q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
         else:
             src = encoder_hidden_states
@@ -100,8 +107,9 @@ class AttnProcessor2_0:
             wkv, bkv = fused_linear_params(attn, "kv", (attn.to_k, attn.to_v))
             kv = ops.conv2d(src.view(src.shape[0], src.shape[1], 1, c), wkv, bkv, 1).view(src.shape[0], src.shape[1], 2 * c)
             k, v = kv[:, :, :c], kv[:, :, c:]
-        d = c // attn.heads
-        if d <= 64 and d % 8 == 0:
+        if q.dtype == torch.float16 and k.dtype == torch.float16:
+            o = ops.attention_f16(q, k, v, attn.heads)
+        elif d <= 64 and d % 8 == 0:
             o = ops.attention(q, k, v, attn.heads)
         else:
             o = ops.attention_gemm(q, k, v, attn.heads)

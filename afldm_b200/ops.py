@@ -310,6 +310,60 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+F16_ATTENTION = os.environ.get("AFLDM_ATTN_F16", "1") == "1"
+
+
+def conv2d_f16out(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], ksize: int) -> Optional[torch.Tensor]:
+    """fp16(conv(x) + bias) on the tcgen05 path (the q | k | v projection in front of ``attention_f16``).
+    Returns None when this shape has no fp16 epilogue (split-K layers, shapes outside the tensor-core family):
+    the caller then uses ``conv2d`` + ``attention``."""
+    _chk(w_packed, "w_packed")
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _lib.AfldmError("conv2d_f16out: fp32 CUDA input expected")
+    b, h, w_, cin = x.shape
+    cout = w_packed.shape[0]
+    x_pitch = _pitch(x)
+    out = torch.empty((b, h, w_, cout), dtype=torch.float16, device=x.device)
+    L = _lib.lib()
+
+    def call():
+        return L.afldm_conv2d_f16out(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), out.data_ptr(), cout,
+                                     b, h, w_, cin, cout, ksize, _stream())
+
+    code = call()
+    if code == -3:
+        return None
+    _lib.check(code, "conv2d_f16out")
+    if _recorder is not None:
+        _recorder.append(("conv2d_tf32", dict(B=b, H=h, W=w_, Cin=cin, Cout=cout, k=ksize, f16out=1,
+                                              flops=2.0 * b * h * w_ * cout * cin * ksize * ksize), call,
+                          (x, w_packed, bias, out)))
+    return out
+
+
+def attention_f16(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``attention`` for fp16 q / k / v (column slices of the fp16 fused-QKV buffer); fp32 output."""
+    b, nq, cd = q.shape
+    bkv, nk, _ = k.shape
+    d = cd // heads
+    for t in (q, k, v):
+        if t.dtype != torch.float16 or not t.is_cuda:
+            raise _lib.AfldmError("attention_f16: fp16 CUDA tensors expected")
+        if t.stride(-1) != 1 or t.stride(0) != t.shape[1] * t.stride(1):
+            raise _lib.AfldmError("attention_f16: rows must be densely pitched")
+    if k.stride(1) != v.stride(1):
+        raise _lib.AfldmError("attention_f16: k and v must share a pitch")
+    if out is None:
+        out = torch.empty((b, nq, cd), dtype=torch.float32, device=q.device)
+    L = _lib.lib()
+    _run("attention_f16", dict(B=b, Nq=nq, Nk=nk, heads=heads, d=d, flops=4.0 * b * heads * nq * nk * d),
+         lambda: L.afldm_attention_f16(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1),
+                                       out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, _stream()),
+         (q, k, v, out))
+    return out
+
+
 def _pitch(t: torch.Tensor) -> int:
     """Pixel pitch (floats) of an NHWC tensor or of a channel slice of a wider NHWC buffer."""
     b, h, w, c = t.shape

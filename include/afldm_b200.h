@@ -145,6 +145,13 @@ AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, cons
                      int algo, float* workspace, size_t workspace_floats, float* gn_partial,
                      afldm_stream_t stream);
 
+/* The tensor-core convolution with an fp16 output (y: IEEE binary16, row pitch y_pitch halves, 8-byte aligned rows):
+ * y = fp16(conv(x) + bias).  Used for the fused to_q | to_k | to_v projection in front of afldm_attention_f16.
+ * AFLDM_E_NOKERNEL when the shape runs split-K or outside the tcgen05 family (callers then use afldm_conv2d_f32
+ * and the fp32-input attention). */
+AFLDM_API int afldm_conv2d_f16out(const float* x, int x_pitch, const float* w, const float* bias, void* y, int y_pitch,
+                        int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
+
 /* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
  * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */
 AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float* bias, float* y,
@@ -162,6 +169,14 @@ AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float*
 AFLDM_API int afldm_attention_f32(const float* q, int q_pitch, const float* k, const float* v, int kv_pitch,
                         float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
                         int algo, afldm_stream_t stream);
+
+/* The same attention with fp16 q / k / v (raw IEEE binary16, pitches in halves, rows 16-byte aligned, d % 8 == 0),
+ * as written by afldm_conv2d_f16out; products on tensor cores with fp32 accumulation, fp32 softmax, fp32 output.
+ * fp16 has the 11 significant bits of the TF32 operands of AFLDM_ATTN_MMA_TF32 (same numeric class) and a narrower
+ * exponent: |q|, |k|, |v| must stay below 65504 (they are linear projections of GroupNorm outputs). */
+AFLDM_API int afldm_attention_f16(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch,
+                        float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                        afldm_stream_t stream);
 
 /* In-place row softmax: x[r][:] = softmax(scale * x[r][:]) over `cols` entries, row pitch `pitch`.
  * Used by the large-head-dim attention (VAE mid block: 1 head of 512) which runs as

@@ -267,6 +267,57 @@ def test_attention_on_fused_qkv_slices():
     assert (tc - want).abs().max().item() < 6e-3
 
 
+@pytest.mark.parametrize("b,bkv,nq,nk,heads,d", [(4, 4, 1024, 1024, 8, 24), (2, 2, 256, 256, 16, 24), (16, 16, 16, 16, 32, 24),
+                                                  (6, 2, 64, 64, 16, 24), (2, 1, 100, 77, 4, 40), (2, 2, 16, 16, 2, 64),
+                                                  (1, 1, 200, 130, 3, 32), (2, 2, 8, 4, 2, 8)])
+def test_attention_f16_vs_sdpa(b, bkv, nq, nk, heads, d):
+    """fp16-operand attention (ldmatrix + mma.m16n8k16): (1) against fp32 SDPA evaluated on the SAME fp16-rounded
+    q / k / v the error is P's 11-bit rounding only (<= 1.5e-3 max); (2) against SDPA on the fp32 inputs it is
+    in the TF32 class (6e-3 max / 6e-4 mean, the bound of the TF32 kernel)."""
+    c = heads * d
+    q, k, v = randn(b, nq, c, seed=1), randn(bkv, nk, c, seed=2), randn(bkv, nk, c, seed=3)
+    qkv_h = [t.half() for t in (q, k, v)]
+    got = ops.attention_f16(*qkv_h, heads)
+    rep = b // bkv
+    sp = lambda t, n: t.view(b, n, heads, d).transpose(1, 2)
+    def sdpa(q_, k_, v_):
+        kk = k_.unsqueeze(1).repeat(1, rep, 1, 1).reshape(b, nk, c)
+        vv = v_.unsqueeze(1).repeat(1, rep, 1, 1).reshape(b, nk, c)
+        return F.scaled_dot_product_attention(sp(q_, nq), sp(kk, nk), sp(vv, nk)).transpose(1, 2).reshape(b, nq, c)
+    same = sdpa(*[t.float() for t in qkv_h])
+    assert (got - same).abs().max().item() < 1.5e-3
+    err = (got - sdpa(q, k, v)).abs()
+    assert err.max().item() < 6e-3 and err.mean().item() < 6e-4, (err.max().item(), err.mean().item())
+
+
+def test_attention_f16_exact_selection_and_qkv_slices():
+    """One-hot softmax on +-64 codes: the fp16 kernel must return the selected V rows exactly (fragment layouts of
+    ldmatrix / ldmatrix.trans); q, k, v are column slices of one fused fp16 buffer as in the attention block."""
+    b, n, heads, d = 2, 192, 3, 24
+    c = heads * d
+    idx = torch.randperm(n, generator=torch.Generator().manual_seed(0)).to(DEV)
+    code = ((torch.arange(n, device=DEV)[:, None] >> torch.arange(d, device=DEV)[None, :]) & 1).float() * 2 - 1
+    qkv = torch.empty(b, n, 3 * c, device=DEV, dtype=torch.float16)
+    qkv[:, :, :c] = (code[idx] * 8.0).repeat(1, heads)
+    qkv[:, :, c:2 * c] = (code * 8.0).repeat(1, heads)
+    vv = ((randn(b, n, c, seed=5) * 16).round() / 16)
+    qkv[:, :, 2 * c:] = vv
+    out = ops.attention_f16(qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:], heads)
+    torch.testing.assert_close(out, vv[:, idx], rtol=0, atol=1e-6)
+
+
+def test_conv2d_f16out_matches_fp32_epilogue():
+    """The fp16-output epilogue of the tcgen05 convolution = fp16 rounding of the fp32 one; split-K shapes decline."""
+    x, wt, bias = randn(16, 192, 32, 32, seed=1), randn(576, 192, 1, 1, seed=2) * 0.07, randn(576, seed=3)
+    xp, wp = x.permute(0, 2, 3, 1).contiguous(), ops.pack_conv_weight(wt)
+    h = ops.conv2d_f16out(xp, wp, bias, 1)
+    assert h is not None and h.dtype == torch.float16
+    ref = ops.conv2d(xp, wp, bias, 1, algo="tf32")
+    assert torch.equal(h, ref.half())
+    xs = randn(16, 768, 2, 2, seed=4).permute(0, 2, 3, 1).contiguous()
+    assert ops.conv2d_f16out(xs, ops.pack_conv_weight(randn(2304, 768, 1, 1, seed=5) * 0.03), None, 1) is None
+
+
 def test_attention_large_head_dim_via_gemm():
     b, n, d = 2, 256, 512
     q, k, v = randn(b, n, d, seed=1) * 0.2, randn(b, n, d, seed=2) * 0.2, randn(b, n, d, seed=3)
