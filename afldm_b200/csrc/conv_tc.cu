@@ -454,6 +454,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * a.BN);
             for (int c = 0; c < a.BN; c += 32) {
+                // Everything the fused epilogue adds (bias + time-embedding row + residual) is fetched BEFORE the
+                // accumulator read, with clamped addresses, so the global-load latency hides under the TMEM load and
+                // the staging transpose instead of serialising the eight store passes (K-light 1x1 layers are
+                // epilogue-bound: profiles/r01_epilogue_notes.md).
+                const bool fast = !split && a.vec_ok && !a.y_half;
+                float4 addv[8];
+                if (fast) {
+                    const int nc = min(n0 + c + cq * 4, a.Cout - 4);
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.bias != nullptr) bv = *reinterpret_cast<const float4*>(a.bias + nc);
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int mmc = min(m0 + q * 32 + pass * 4 + rsub, a.M - 1);
+                        float4 t = bv;
+                        if (a.row_add != nullptr) {
+                            const float4 u = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mmc / a.HW) * a.row_add_pitch + nc);
+                            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                        }
+                        if (a.residual != nullptr) {
+                            const float4 u = *reinterpret_cast<const float4*>(a.residual + (size_t)mmc * a.res_pitch + nc);
+                            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                        }
+                        addv[pass] = t;
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld32(tacc + (uint32_t)c, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -473,6 +498,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     srow[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
                                            __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
                 __syncwarp();
+                if (a.y_half) {
+                    // fp16 output (no residual / GroupNorm sums on this path): 4 lanes x 8 columns per row, 8 rows per
+                    // pass, one 16-byte store per lane
+                    const int cq8 = lane & 3, rs8 = lane >> 2;
+                    const int n8 = n0 + c + cq8 * 8;
+#pragma unroll
+                    for (int pass = 0; pass < 4; ++pass) {
+                        const int rr = pass * 8 + rs8;
+                        const int mm = m0 + q * 32 + rr;
+                        if (mm >= a.M || n8 >= a.Cout || c + cq8 * 8 >= a.BN) continue;
+                        float4 v0 = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + cq8 * 8);
+                        float4 v1 = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + cq8 * 8 + 4);
+                        if (a.bias != nullptr) {
+                            const float4 t0 = *reinterpret_cast<const float4*>(a.bias + n8);
+                            const float4 t1 = *reinterpret_cast<const float4*>(a.bias + n8 + 4);
+                            v0.x += t0.x; v0.y += t0.y; v0.z += t0.z; v0.w += t0.w;
+                            v1.x += t1.x; v1.y += t1.y; v1.z += t1.z; v1.w += t1.w;
+                        }
+                        if (a.row_add != nullptr) {
+                            const float* rp = a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n8;
+                            const float4 t0 = *reinterpret_cast<const float4*>(rp);
+                            const float4 t1 = *reinterpret_cast<const float4*>(rp + 4);
+                            v0.x += t0.x; v0.y += t0.y; v0.z += t0.z; v0.w += t0.w;
+                            v1.x += t1.x; v1.y += t1.y; v1.z += t1.z; v1.w += t1.w;
+                        }
+                        const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+                        const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.y) + (size_t)mm * a.y_pitch + n8) = pk;
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 // ... and write it out 4 rows x 128 contiguous bytes per instruction
                 const int n = n0 + c + cq * 4;
                 float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -485,27 +547,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (split) {
                         *reinterpret_cast<float4*>(a.ws + ((size_t)z * a.M + mm) * a.Cout + n) = v;
                     } else if (a.vec_ok) {
-                        if (a.bias != nullptr) {
-                            const float4 t = *reinterpret_cast<const float4*>(a.bias + n);
-                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                        }
-                        if (a.row_add != nullptr) {
-                            const float4 t = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n);
-                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                        }
-                        if (a.residual != nullptr) {
-                            const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
-                            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-                        }
-                        if (a.y_half) {
-                            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-                            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.y) + (size_t)mm * a.y_pitch + n) = pk;
-                        } else {
-                            *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
-                        }
+                        const float4 t = addv[pass];
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
                         gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
                         gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
                         gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
@@ -752,8 +796,9 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
                    int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
                    cudaStream_t st, int y_half) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
-    if (y_half && (!p.ok || p.splitk > 1 || residual != nullptr || gn_partial != nullptr || (Cout & 3) != 0 ||
-                   (y_pitch & 3) != 0 || (reinterpret_cast<uintptr_t>(y) & 7u) != 0))
+    if (y_half && (!p.ok || p.splitk > 1 || residual != nullptr || gn_partial != nullptr || (Cout & 7) != 0 ||
+                   (y_pitch & 7) != 0 || !aligned16(y) || (bias != nullptr && !aligned16(bias)) ||
+                   (row_add != nullptr && ((row_add_pitch & 3) != 0 || !aligned16(row_add)))))
         return AFLDM_E_NOKERNEL;             // fp16 stores live in the vectorised un-split epilogue only
     const int gn_slots = gn_partial != nullptr ? conv_tc_gn_slots(B, H, W, Cin, Cout, ks) : 0;
     if (gn_partial != nullptr && gn_slots == 0) return AFLDM_E_SHAPE;

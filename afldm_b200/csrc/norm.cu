@@ -9,6 +9,8 @@
 //                (consecutive threads = consecutive channels of a pixel, then the next pixel), fp32
 //                partial sums per thread, fp64 block reduction, then the group's channels get their
 //                scale / shift.  One launch, no scratch, fixed reduction order (deterministic).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace afldm {
@@ -149,6 +151,87 @@ affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
     }
 }
 
+// GroupNorm finalisation + y = act(x * scale + shift) in ONE launch (normalised input of an attention block):
+// every CTA first turns the producer's partial sums of ITS image into per-channel scale / shift in shared memory
+// (one warp per group, fp32 adds, fp64 only for E[x^2] - mean^2; a few KB of L2-resident loads), then streams its
+// slice of the image.  Replaces gn_finalize_kernel + affine_act_kernel (two launches and their gap).
+template <int ACT>
+__global__ void __launch_bounds__(1024)
+affine_act_gn_kernel(const float4* __restrict__ x, float4* __restrict__ y, int HW, int C,
+                     const float2* __restrict__ pa, int slots_a, int Ca, const float2* __restrict__ pb, int slots_b,
+                     int Cb, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                     double inv_n) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float s_aff[];                  // [C] scale | [C] shift | [groups] mean | [groups] rstd
+    float* s_sc = s_aff;
+    float* s_sh = s_aff + C;
+    float* s_mean = s_aff + 2 * C;
+    float* s_rstd = s_mean + groups;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int cpg = C / groups;
+    const int slots_max = max(slots_a, slots_b);
+    const int total = slots_max * cpg;
+    for (int g = warp; g < groups; g += nwarps) {
+        float s = 0.f, q = 0.f;
+        for (int it0 = lane; it0 < total; it0 += 128) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + 32 * u;
+                const int sl = it / cpg, cc = g * cpg + (it - sl * cpg);
+                v[u] = make_float2(0.f, 0.f);
+                if (it < total) {
+                    if (cc < Ca) {
+                        if (sl < slots_a) v[u] = __ldg(&pa[((size_t)b * slots_a + sl) * Ca + cc]);
+                    } else {
+                        if (sl < slots_b) v[u] = __ldg(&pb[((size_t)b * slots_b + sl) * Cb + (cc - Ca)]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s += v[u].x;
+                q += v[u].y;
+            }
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if (lane == 0) {
+            const double mean = (double)s * inv_n;
+            double var = (double)q * inv_n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = (float)mean;
+            s_rstd[g] = rsqrtf((float)var + eps);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = (gamma != nullptr ? gamma[c] : 1.f) * s_rstd[g];
+        s_sc[c] = sc;
+        s_sh[c] = fmaf(-s_mean[g], sc, beta != nullptr ? beta[c] : 0.f);
+    }
+    __syncthreads();
+    const int C4 = C >> 2;
+    const long long per_image4 = (long long)HW * C4;
+    const float4* xb = x + (size_t)b * per_image4;
+    float4* yb = y + (size_t)b * per_image4;
+    const float4* sc4 = reinterpret_cast<const float4*>(s_sc);
+    const float4* sh4 = reinterpret_cast<const float4*>(s_sh);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_image4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = xb[i];
+        const int c4 = (int)(i % C4);
+        const float4 sc = sc4[c4], sh = sh4[c4];
+        v.x = apply_act<ACT>(fmaf(v.x, sc.x, sh.x));
+        v.y = apply_act<ACT>(fmaf(v.y, sc.y, sh.y));
+        v.z = apply_act<ACT>(fmaf(v.z, sc.z, sh.z));
+        v.w = apply_act<ACT>(fmaf(v.w, sc.w, sh.w));
+        yb[i] = v;
+    }
+}
+
 }  // namespace
 }  // namespace afldm
 
@@ -201,6 +284,38 @@ extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int
     else if (act == AFLDM_ACT_IDENTITY)
         launch_k(affine_act_kernel<AFLDM_ACT_IDENTITY>, dim3(blocks), dim3(256), 0, st, 
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh);
+    else
+        return AFLDM_E_ARG;
+    return launched();
+}
+
+extern "C" int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, int C, int act,
+                                       const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                       int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                       const float* beta, afldm_stream_t stream) {
+    if (x == nullptr || y == nullptr || partial_a == nullptr || B <= 0 || HW <= 0 || C <= 0) return AFLDM_E_ARG;
+    if (slots_a <= 0 || Ca <= 0 || Cb < 0 || groups <= 0 || (Cb > 0 && (partial_b == nullptr || slots_b <= 0)))
+        return AFLDM_E_ARG;
+    if (Ca + Cb != C || C % groups != 0 || C % 4 != 0 || B > 65535) return AFLDM_E_SHAPE;
+    if (!aligned16(x) || !aligned16(y)) return AFLDM_E_ARG;
+    const size_t smem = (size_t)(2 * C + 2 * groups) * sizeof(float);
+    if (smem > 48 * 1024) return AFLDM_E_SHAPE;
+    const long long per_image4 = (long long)HW * C / 4;
+    // about two waves of 1024-thread CTAs over the batch; at least one CTA per image
+    int chunks = (int)std::min<long long>((per_image4 + 1023) / 1024, std::max(1, 2 * 148 / B));
+    if (chunks < 1) chunks = 1;
+    const double inv_n = 1.0 / ((double)HW * (double)(C / groups));
+    cudaStream_t st = as_stream(stream);
+    auto pa = reinterpret_cast<const float2*>(partial_a);
+    auto pb = reinterpret_cast<const float2*>(partial_b);
+    auto x4 = reinterpret_cast<const float4*>(x);
+    auto y4 = reinterpret_cast<float4*>(y);
+    if (act == AFLDM_ACT_SILU)
+        launch_k(affine_act_gn_kernel<AFLDM_ACT_SILU>, dim3(chunks, B), dim3(1024), smem, st, x4, y4, HW, C, pa, slots_a, Ca,
+                 pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n);
+    else if (act == AFLDM_ACT_IDENTITY)
+        launch_k(affine_act_gn_kernel<AFLDM_ACT_IDENTITY>, dim3(chunks, B), dim3(1024), smem, st, x4, y4, HW, C, pa, slots_a,
+                 Ca, pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n);
     else
         return AFLDM_E_ARG;
     return launched();

@@ -25,8 +25,7 @@ def _conv(m: nn.Conv2d, x_nchw: torch.Tensor) -> torch.Tensor:
 
 def _norm_act_conv(norm: nn.GroupNorm, act: nn.Module, conv: nn.Conv2d, x_nchw: torch.Tensor) -> torch.Tensor:
     x = ops.nhwc(x_nchw)
-    scale, shift = ops.groupnorm_affine(x, norm.num_groups, norm.eps, norm.weight, norm.bias)
-    a = ops.affine_act(x, scale, shift, act=act_name(act))
+    a = ops.groupnorm_act(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=act_name(act))
     w, b, k = conv_params(conv)
     return ops.nchw_view(ops.conv2d(a, w, b, k))
 

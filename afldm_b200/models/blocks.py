@@ -27,8 +27,7 @@ def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module) -> to
     A ``WarpedNonlinearity`` (alias-free surgery) selects the filtered activation."""
     if isinstance(nonlinearity, WarpedNonlinearity):
         return ops.filtered_act_groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=nonlinearity.act)
-    scale, shift = ops.groupnorm_affine(x, norm.num_groups, norm.eps, norm.weight, norm.bias)
-    return ops.affine_act(x, scale, shift, act=act_name(nonlinearity))
+    return ops.groupnorm_act(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=act_name(nonlinearity))
 
 
 class ResnetBlock2D(nn.Module):
@@ -84,8 +83,7 @@ class AttnProcessor2_0:
         xn = x
         if attn.group_norm is not None:
             gn = attn.group_norm
-            scale, shift = ops.groupnorm_affine(x, gn.num_groups, gn.eps, gn.weight, gn.bias)
-            xn = ops.affine_act(x, scale, shift, act="identity")
+            xn = ops.groupnorm_act(x, gn.num_groups, gn.eps, gn.weight, gn.bias, act="identity")
         d = c // attn.heads
         # TF32 class: the projections may hand q | k | v over as fp16 (same 11-bit significands as TF32 operands)
         # to the ldmatrix / mma.m16n8k16 attention kernel

@@ -160,8 +160,7 @@ class UNet2DModel(nn.Module):
 
         hx = ops.nhwc(h)
         gn = self.conv_norm_out
-        scale, shift = ops.groupnorm_affine(hx, gn.num_groups, gn.eps, gn.weight, gn.bias)
-        a = ops.affine_act(hx, scale, shift, act=act_name(self.conv_act))       # conv_act is NOT wrapped
+        a = ops.groupnorm_act(hx, gn.num_groups, gn.eps, gn.weight, gn.bias, act=act_name(self.conv_act))   # conv_act is NOT wrapped
         w, b, k = conv_params(self.conv_out)
         out = ops.nchw_view(ops.conv2d(a, w, b, k))
         return UNet2DOutput(out) if return_dict else (out,)

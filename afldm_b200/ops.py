@@ -247,6 +247,28 @@ def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[t
     return out
 
 
+def groupnorm_act(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
+                  beta: Optional[torch.Tensor], act: str = "identity") -> torch.Tensor:
+    """act(GroupNorm(x)) materialised (the normalised input of an attention block).  One launch when the producer
+    of x emitted its GroupNorm partial sums (``FUSE_GN_PROLOGUE``), else statistics / finalize + ``affine_act``."""
+    _chk(x, "x")
+    b, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (b * c)
+    one, two = getattr(x, "_afldm_gn", None), getattr(x, "_afldm_gn2", None)
+    if FUSE_GN_PROLOGUE and (one is not None or two is not None) and c % 4 == 0 and 2 * c + 2 * groups <= 12288:
+        (pa, sa, ca), (pb, sb, cb) = (one, (None, 0, 0)) if one is not None else two
+        if ca + cb == c:
+            out = torch.empty_like(x)
+            L = _lib.lib()
+            _run("affine_act", dict(elems=x.numel(), fused_gn=1),
+                 lambda: L.afldm_affine_act_gn_f32(x.data_ptr(), out.data_ptr(), b, hw, c, ACT[act], pa.data_ptr(), sa, ca,
+                                                   _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma), _ptr(beta),
+                                                   _stream()), (x, out, pa, pb, gamma, beta))
+            return out
+    scale, shift = groupnorm_affine(x, groups, eps, gamma, beta)
+    return affine_act(x, scale, shift, act=act)
+
+
 # ------------------------------------------------------------------------- conv / linear
 def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     """nn.Conv2d weight [Cout,Cin,kh,kw] (or nn.Linear [Cout,Cin]) -> packed [Cout][kh*kw][Cin]."""

@@ -65,8 +65,7 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
             x = x.view(x.shape[0], x.shape[1], 1, x.shape[2])
         if attn.group_norm is not None:
             gn = attn.group_norm
-            scale, shift = ops.groupnorm_affine(x, gn.num_groups, gn.eps, gn.weight, gn.bias)
-            x = ops.affine_act(x, scale, shift, act="identity")
+            x = ops.groupnorm_act(x, gn.num_groups, gn.eps, gn.weight, gn.bias, act="identity")
         return x.view(x.shape[0], x.shape[1], x.shape[3])
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,

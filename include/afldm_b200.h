@@ -119,6 +119,14 @@ AFLDM_API int afldm_groupnorm_finalize_f32(const float* partial_a, int slots_a, 
 AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,
                          const float* scale, const float* shift, afldm_stream_t stream);
 
+/* GroupNorm (finalised from the producer's partial sums, as in afldm_groupnorm_finalize_f32) and
+ * y = act(x*scale + shift) in one launch: the normalised input of an attention block
+ * (diffusers Attention.group_norm in AttnProcessor2_0) without a separate finalize kernel. */
+AFLDM_API int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, int C, int act,
+                            const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                            int slots_b, int Cb, int groups, float eps, const float* gamma,
+                            const float* beta, afldm_stream_t stream);
+
 /* ---- convolution / linear as implicit GEMM -----------------------------------------------
  * nn.Conv2d(Cin, Cout, k, stride=1, padding=k/2) with k in {1,3} on NHWC input, fused epilogue:
  *   y[b,h,w,:] = conv(x)[b,h,w,:] + bias + row_add[b,:] + residual[b,h,w,:]

@@ -120,15 +120,18 @@ def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
         # GroupNorm finalised inside the filtered-activation kernel == statistics pass + filtered activation
         rec = []
         ops.record_to(rec)
-        ops.FUSE_GN_PROLOGUE = True
+        prev, ops.FUSE_GN_PROLOGUE = ops.FUSE_GN_PROLOGUE, True
         try:
             fa1 = ops.filtered_act_groupnorm(y, 32, 1e-5, gamma, beta)
+            na1 = ops.groupnorm_act(y, 32, 1e-5, gamma, beta, act="silu")
         finally:
-            ops.FUSE_GN_PROLOGUE = False
+            ops.FUSE_GN_PROLOGUE = prev
             ops.record_to(None)
-        assert [r[0] for r in rec] == ["filtered_act"]                       # one launch
+        assert [r[0] for r in rec] == ["filtered_act", "affine_act"]         # one launch each
         fa0 = ops.filtered_act(y, s0, t0)
         torch.testing.assert_close(fa1, fa0, rtol=0, atol=3e-5)
+        # GroupNorm finalised inside the normalise-and-activate kernel (attention input, VAE / tail SiLU)
+        torch.testing.assert_close(na1, ops.affine_act(y, s0, t0, act="silu"), rtol=0, atol=3e-5)
     # through the zero-copy layout views and a channel concat of two producers
     v = ops.nhwc(ops.nchw_view(y))
     assert hasattr(v, "_afldm_gn")
@@ -140,6 +143,12 @@ def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
     sr, tr = ops.groupnorm_affine(cat.clone(), 32, 1e-5, g2, b2)
     torch.testing.assert_close(sc, sr, rtol=2e-5, atol=1e-6)
     torch.testing.assert_close(tc, tr, rtol=0, atol=2e-5)
+    prev, ops.FUSE_GN_PROLOGUE = ops.FUSE_GN_PROLOGUE, True
+    try:
+        n2 = ops.groupnorm_act(cat, 32, 1e-5, g2, b2, act="identity")          # two-source partial sums
+    finally:
+        ops.FUSE_GN_PROLOGUE = prev
+    torch.testing.assert_close(n2, ops.affine_act(cat, sr, tr, act="identity"), rtol=0, atol=3e-5)
     if h <= 32:
         torch.testing.assert_close(ops.filtered_act_groupnorm(cat, 32, 1e-5, g2, b2), ops.filtered_act(cat, sr, tr),
                                    rtol=0, atol=3e-5)
