@@ -173,7 +173,7 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, one MUFU; -i
 }
 
 // MT = 16-row query tiles per warp: 2 for long sequences (every K / V fragment read from shared memory feeds
-// two MMAs; ncu on the MT = 1 version showed ~700 issued instructions per 48 HMMA, profiles/r02_ncu_attention.md),
+// two MMAs; ncu on the MT = 1 version showed ~700 issued instructions per 48 HMMA, profiles/r01_ncu_attention.md),
 // 1 for short ones (more CTAs).  K fragments are read as 64-bit words: MMA k-index t <- head-dim column 2t,
 // t + 4 <- 2t + 1 inside each 8-column chunk, the Q fragment uses the same permutation.
 template <int D, int MT>

@@ -695,9 +695,15 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     const int tiles = p.mtiles * p.ntiles;
     int s = 1;
     if (tiles < 100) {
-        s = ceil_div(2 * 148, tiles);
-        s = std::min(s, std::max(1, p.total_iters / 4));   // >= 4 stages of 32 k per split
+        // Split K until at most one wave of CTAs exists, but keep >= 8 stages per split, and do not split K-light
+        // 1x1 layers that already have >= 32 tiles: their whole main loop is <= 24 stages, shorter than the
+        // second launch (deterministic reduce) a split costs.  From a forced-split sweep over every small-M layer
+        // of the step on B200 (profiles/r01_conv_splitk_sweep.md): -0.12 ms per step against "two waves, >= 4 stages".
+        s = std::max(1, num_sms() / tiles);                // floor: tiles * s CTAs never spill into a second,
+                                                           // nearly empty wave (160 CTAs on 148 SMs = 2x the time)
+        s = std::min(s, std::max(1, p.total_iters / 8));
         s = std::min(s, 64);
+        if (ks == 1 && tiles >= 32) s = 1;
     }
     if (force_split > 0) s = std::min(force_split, p.total_iters);
     if (Cout % 4 != 0) s = 1;            // split-K partials are written as float4
@@ -726,7 +732,7 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
         }
         // 3x3 layers that run in halo mode (below): 96 columns.  With the activation bytes cut by the halo box the
         // weight half-tile dominates the ingest, and 96 beats both 64 (more weight bytes per FLOP) and 128 / 192
-        // (60 KB stages, 3-deep ring) on every 16x16 / 32x32 layer of the step (profiles/r02_conv_knobs.md).
+        // (60 KB stages, 3-deep ring) on every 16x16 / 32x32 layer of the step (profiles/r01_conv_knobs.md).
         if (ks == 3 && p.BB == 1 && p.BH >= 2 && Cout % 96 == 0) bn2 = 96;
         if (ks != 3 && bn2 < 128) bn2 = 0;
         if (force_bn2 > 0) bn2 = (Cout % force_bn2 == 0 && force_bn2 % 16 == 0 && force_bn2 <= 256) ? force_bn2 : 0;
@@ -739,7 +745,7 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     // Halo mode: un-split 3x3 layers whose 128-pixel tile is BH >= 2 whole rows of one image (W = 16 ... 64).
     static const int allow_halo = getenv("AFLDM_TC_HALO") ? atoi(getenv("AFLDM_TC_HALO")) : 1;
     // Not for the widest CTA-pair tiles: those layers already run tensor-bound (fewest bytes per FLOP) and the
-    // 60 KB halo stages leave a 3-deep ring (sweep on B200, profiles/r02_conv_halo_sweep.md: 68.9 vs 63.2 us).
+    // 60 KB halo stages leave a 3-deep ring (sweep on B200, profiles/r01_conv_halo_sweep.md: 68.9 vs 63.2 us).
     p.halo = (allow_halo && ks == 3 && p.splitk == 1 && p.BB == 1 && p.BH >= 2 && p.BW >= 8 && p.BW * p.BH == TBM &&
               !(p.two && p.BN >= 192 && allow_halo < 2)) ? 1 : 0;
     const int b_bytes = (p.two ? p.BN / 2 : p.BN) * TBK * 4;
