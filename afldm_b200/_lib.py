@@ -30,6 +30,7 @@ SIGNATURES = {
     "afldm_filtered_act_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
     "afldm_up2_ideal_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "afldm_lpf_down2_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "afldm_lpf_down2_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "afldm_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
     "afldm_groupnorm_affine_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "afldm_affine_act_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),

@@ -85,4 +85,4 @@ class AliasFreeDownsample2D(nn.Module):
         # padding == 1: the conv pads itself.  Both are the same "same"-size 3x3 convolution.
         w, b, k = conv_params(self.conv)
         h = ops.conv2d(ops.nhwc(hidden_states), w, b, k)
-        return ops.nchw_view(ops.lpf_down2(h))
+        return ops.nchw_view(ops.lpf_down2(h, gn_stats=True))

@@ -668,7 +668,8 @@ int launch_f16_mt(const __half* q, int q_pitch, const __half* k, const __half* v
 template <int D>
 int launch_f16(const __half* q, int q_pitch, const __half* k, const __half* v, int kv_pitch, float* o, int o_pitch,
                int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
-    if (D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
+    static const int force_mt = getenv("AFLDM_ATTN_MT") ? atoi(getenv("AFLDM_ATTN_MT")) : 0;
+    if (force_mt != 1 && D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
         return launch_f16_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
     return launch_f16_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
 }

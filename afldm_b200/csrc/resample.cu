@@ -101,6 +101,7 @@ struct Affine {
     int slots_a, Ca, slots_b, Cb, groups, HW;
     float eps;
     double inv_n;         // 1 / (HW * channels per group), from the host: no fp64 division in the prologue
+    float2* gn_out;       // MODE_DOWN2 only: [B][1][C] (sum, sum of squares) of every output plane | NULL
 };
 
 // One warp per GroupNorm group touched by this CTA's CG channels (at most CG of them): the partial sums are added
@@ -174,6 +175,7 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
     pdl_wait();
     extern __shared__ float tile[];
     __shared__ float s_sc[CG], s_sh[CG];
+    __shared__ float2 s_gn[MODE == MODE_DOWN2 ? N * CG : 1];
     if (MODE != MODE_DOWN2 && af.pa != nullptr) gn_prologue<CG>(af, blockIdx.y, blockIdx.x * CG, C, s_sc, s_sh);
     constexpr int PITCH = Tile<N, CG>::PITCH;
     constexpr int M = 2 * N;
@@ -255,6 +257,32 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
         float* yp = y + ((size_t)(b * N + i) * N) * C + c0 + c;
 #pragma unroll
         for (int j = 0; j < N; ++j) yp[(size_t)j * C] = yl[j];
+        if constexpr (MODE == MODE_DOWN2) {
+            if (af.gn_out != nullptr) {
+                float ps = 0.f, pq = 0.f;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    ps += yl[j];
+                    pq = fmaf(yl[j], yl[j], pq);
+                }
+                s_gn[i * CG + c] = make_float2(ps, pq);
+            }
+        }
+    }
+    if constexpr (MODE == MODE_DOWN2) {
+        // GroupNorm partial sums of the output plane (one slot per image): the next resnet's norm needs no pass
+        // over y.  Rows are added in a fixed order (deterministic).
+        if (af.gn_out != nullptr) {
+            __syncthreads();
+            for (int c = threadIdx.x; c < CG; c += blockDim.x) {
+                float ps = 0.f, pq = 0.f;
+                for (int i = 0; i < N; ++i) {
+                    ps += s_gn[i * CG + c].x;
+                    pq += s_gn[i * CG + c].y;
+                }
+                af.gn_out[(size_t)b * C + c0 + c] = make_float2(ps, pq);
+            }
+        }
     }
 }
 
@@ -779,4 +807,14 @@ extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W
         return resample_large(MODE_DOWN2, AFLDM_ACT_IDENTITY, x, y, B, H, C, nullptr, nullptr, workspace,
                               workspace_floats, st);
     return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, plain_affine(nullptr, nullptr), st);
+}
+
+extern "C" int afldm_lpf_down2_gn_f32(const float* x, float* y, int B, int H, int W, int C, float* gn_partial,
+                                      afldm_stream_t stream) {
+    if (bad_args(x, y, B, H, W, C, nullptr, nullptr) || x == y || gn_partial == nullptr) return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;
+    if (H > 16) return AFLDM_E_NOKERNEL;      // statistics are emitted by the register-resident kernels (n <= 16)
+    Affine af = plain_affine(nullptr, nullptr);
+    af.gn_out = reinterpret_cast<float2*>(gn_partial);
+    return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, as_stream(stream));
 }

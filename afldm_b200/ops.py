@@ -188,14 +188,22 @@ def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
     return out
 
 
-def lpf_down2(x: torch.Tensor) -> torch.Tensor:
-    """LPF_RFFT(0.5)(x)[..., ::2, ::2] (af_blocks.py:149-150) on NHWC x."""
+def lpf_down2(x: torch.Tensor, gn_stats: bool = False) -> torch.Tensor:
+    """LPF_RFFT(0.5)(x)[..., ::2, ::2] (af_blocks.py:149-150) on NHWC x.  ``gn_stats``: also emit the GroupNorm
+    partial sums of the output (attached to the returned tensor, as ``conv2d(gn_stats=True)`` does)."""
     _chk(x, "x")
     b, h2, w2, c = x.shape
     if h2 % 2 or w2 % 2:
         raise _lib.AfldmError("lpf_down2: even input size expected")
     out = torch.empty((b, h2 // 2, w2 // 2, c), dtype=torch.float32, device=x.device)
     L = _lib.lib()
+    if gn_stats and h2 // 2 <= 16 and h2 == w2:
+        gn = torch.empty((b, 1, c, 2), dtype=torch.float32, device=x.device)
+        _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel(), gn=1),
+             lambda: L.afldm_lpf_down2_gn_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, gn.data_ptr(),
+                                              _stream()), (x, out, gn))
+        out._afldm_gn = (gn, 1, c)
+        return out
     need = L.afldm_resample_workspace_floats(2, b, h2 // 2, w2 // 2, c)
     ws = scratch(x.device, need) if need else None
     _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel()),

@@ -92,6 +92,11 @@ AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W,
  * x NHWC [B,2H,2W,C] -> y NHWC [B,H,W,C]  (H, W are the OUTPUT sizes). */
 AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,
                         size_t workspace_floats, afldm_stream_t stream);
+/* The same, also emitting the GroupNorm partial sums of y (gn_partial [B][1][C] float2 = (sum, sum of squares) per
+ * output plane, the format afldm_groupnorm_finalize_f32 / afldm_filtered_act_gn_f32 consume with slots = 1), so the
+ * resnet that follows a down-sampler needs no statistics pass.  Output planes up to 16 x 16. */
+AFLDM_API int afldm_lpf_down2_gn_f32(const float* x, float* y, int B, int H, int W, int C, float* gn_partial,
+                           afldm_stream_t stream);
 
 /* ---- GroupNorm ----------------------------------------------------------------------------
  * torch.nn.GroupNorm(groups, C, eps) as used by diffusers ResnetBlock2D / Attention

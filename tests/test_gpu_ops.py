@@ -109,6 +109,25 @@ def test_up2_and_lpf_down2_vs_oracle(n, c):
     torch.testing.assert_close(dn, OL.lpf_rfft(y)[:, :, ::2, ::2], rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,c,b", [(16, 192, 16), (8, 384, 3), (4, 384, 2), (2, 768, 16)])
+def test_lpf_down2_emits_groupnorm_partials(n, c, b):
+    """The down-sampler's optional GroupNorm partial sums (one slot per output plane): same y, and the finalised
+    scale / shift equal the statistics pass over y."""
+    x = randn(b, 2 * n, 2 * n, c, seed=n)
+    y0 = ops.lpf_down2(x)
+    y1 = ops.lpf_down2(x, gn_stats=True)
+    assert torch.equal(y0, y1) and hasattr(y1, "_afldm_gn")
+    gamma, beta = randn(c, seed=5) * 0.2 + 1, randn(c, seed=6) * 0.2
+    rec = []
+    ops.record_to(rec)
+    s1, t1 = ops.groupnorm_affine(y1, 32, 1e-5, gamma, beta)
+    ops.record_to(None)
+    assert [r[0] for r in rec] == ["groupnorm_finalize"]
+    s0, t0 = ops.groupnorm_affine(y0, 32, 1e-5, gamma, beta)
+    torch.testing.assert_close(s1, s0, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(t1, t0, rtol=0, atol=2e-5)
+
+
 @pytest.mark.parametrize("n,c,b", [(64, 64, 2), (128, 32, 1), (64, 32, 3)])
 def test_large_plane_resamplers_vs_oracle(n, c, b):
     """n = 64 / 128 (VAE decoder, 64x64-latent UNets): three line passes through a workspace."""
@@ -314,8 +333,8 @@ def test_conv2d_f16out_matches_fp32_epilogue():
     assert h is not None and h.dtype == torch.float16
     ref = ops.conv2d(xp, wp, bias, 1, algo="tf32")
     assert torch.equal(h, ref.half())
-    xs = randn(16, 768, 2, 2, seed=4).permute(0, 2, 3, 1).contiguous()
-    assert ops.conv2d_f16out(xs, ops.pack_conv_weight(randn(2304, 768, 1, 1, seed=5) * 0.03), None, 1) is None
+    xs = randn(16, 768, 2, 2, seed=4).permute(0, 2, 3, 1).contiguous()       # 3x3 at the 2x2 level: split-K
+    assert ops.conv2d_f16out(xs, ops.pack_conv_weight(randn(768, 768, 3, 3, seed=5) * 0.03), None, 3) is None
 
 
 def test_attention_large_head_dim_via_gemm():

@@ -28,7 +28,8 @@ def main():
     starts = [i for i, d in enumerate(L) if "timestep_embedding" in d["name"]]
     if len(starts) < 2:
         raise SystemExit(f"need two step starts in the capture window, found {starts} in {len(L)} launches")
-    step = L[starts[0]:starts[1]]
+    step = L[starts[-2]:starts[-1]]          # the last complete step of the capture: a CUDA-graph replay, not the
+                                             # eager recording pass (which also packs weights once)
 
     def short(n):
         n = n.replace("void ", "").replace("afldm::", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
@@ -51,7 +52,7 @@ def main():
     open(out_csv, "w").write("\n".join(out) + "\n")
     conv = [v for k, v in agg.items() if k.startswith("conv_tc_kernel") or k.startswith("splitk_reduce")]
     n_main = sum(v[0] for k, v in agg.items() if k.startswith("conv_tc_kernel"))
-    fact = [v for k, v in agg.items() if "resample" in k and k.rstrip(">").endswith(", 0, 1")]
+    fact = [v for k, v in agg.items() if ("resample" in k and k.rstrip(">").endswith(", 0, 1")) or k.startswith("fact_mma_kernel")]
     json.dump({
         "source": f"{out_csv} (ncu dram__bytes_read.sum + dram__bytes_write.sum, one step)",
         "conv2d_tf32": {"launches": n_main, "dram_bytes_per_step": sum(v[2] for v in conv),
