@@ -34,6 +34,6 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks);
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,
                    int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
-                   cudaStream_t st, int y_half = 0);
+                   cudaStream_t st, int y_half = 0, const float* x2 = nullptr, int x2_pitch = 0, int Cin1 = 0);
 
 }  // namespace afldm

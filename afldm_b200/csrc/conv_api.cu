@@ -63,3 +63,16 @@ extern "C" int afldm_conv2d_f16out(const float* x, int x_pitch, const float* w, 
     return conv_tc_launch(x, x_pitch, w, bias, nullptr, 0, nullptr, 0, static_cast<float*>(y), y_pitch, B, H, W, Cin, Cout,
                           ksize, nullptr, 0, nullptr, as_stream(stream), 1);
 }
+
+extern "C" int afldm_conv2d_cat_f32(const float* xa, int xa_pitch, int Ca, const float* xb, int xb_pitch, int Cb,
+                                    const float* w, const float* bias, const float* row_add, int row_add_pitch,
+                                    const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,
+                                    int Cout, int ksize, float* workspace, size_t workspace_floats, float* gn_partial,
+                                    afldm_stream_t stream) {
+    if (xb == nullptr || Ca <= 0 || Cb <= 0 || xa_pitch < Ca || xb_pitch < Cb) return AFLDM_E_ARG;
+    if (conv_bad_args(xa, xa_pitch, w, y, y_pitch, row_add, row_add_pitch, residual, res_pitch, B, H, W, Ca, Cout, ksize))
+        return AFLDM_E_ARG;
+    if (xb == y) return AFLDM_E_ARG;
+    return conv_tc_launch(xa, xa_pitch, w, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Ca + Cb,
+                          Cout, ksize, workspace, workspace_floats, gn_partial, as_stream(stream), 0, xb, xb_pitch, Ca);
+}

@@ -187,6 +187,7 @@ struct TcArgs {
     int alias_staging;              // one item per CTA: the epilogue staging reuses the (then idle) stage ring
     int halo;                       // 3x3 halo mode: one A box {32 ch, BW, BH + 2} per (kw, channel chunk) serves the 3 kh taps
     int y_half;                     // y is fp16 (y_pitch in halves): QKV projections feeding afldm_attention_f16
+    int cin1_chunks;                // channel chunks [0, cin1_chunks) come from map_a, the rest from map_a2 (un-materialised concat)
 };
 
 // One lane of a converged warp (elect.sync); the same lane every time for the full mask.
@@ -220,8 +221,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {      // bar:
 // the measured bound of the main loop, buys up to 2x the FLOPs.
 template <bool TWO, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static smem: the ring starts 1024-aligned
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t smem_base = smem_u32(smem_raw);
@@ -281,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -341,7 +343,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 int chunk = it_beg - tap * a.cin_chunks;
                 for (int it = it_beg; it < it_end; ++it) {
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    const int c0 = chunk * TBK;
+                    const bool second = chunk >= a.cin1_chunks;
+                    const CUtensorMap* const ma = second ? &map_a2 : &map_a;
+                    const int c0 = (second ? chunk - a.cin1_chunks : chunk) * TBK;     // channel inside its source
                     const uint32_t fb = smem_u32(&full_bar[s]);
                     const uint32_t sa = smem_base + s * stage_bytes;
                     if (elect_one()) {
@@ -352,13 +356,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const int kstep = 3 * a.cin_chunks * TBK;
                             if constexpr (TWO) {
                                 if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
-                                tma2_load_4d(sa, &map_a, fb, c0, w0 + tap - 1, h0 - 1, b0);
+                                tma2_load_4d(sa, ma, fb, c0, w0 + tap - 1, h0 - 1, b0);
 #pragma unroll
                                 for (int kh = 0; kh < 3; ++kh)
                                     tma2_load_2d(sa + a_bytes + kh * b_stage_bytes, &map_b, fb, kb + kh * kstep, nb0);
                             } else {
                                 mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                                tma_load_4d(sa, &map_a, fb, c0, w0 + tap - 1, h0 - 1, b0);
+                                tma_load_4d(sa, ma, fb, c0, w0 + tap - 1, h0 - 1, b0);
 #pragma unroll
                                 for (int kh = 0; kh < 3; ++kh)
                                     tma_load_2d(sa + a_bytes + kh * b_stage_bytes, &map_b, fb, kb + kh * kstep, nb0);
@@ -369,11 +373,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if constexpr (TWO) {
                                 // both CTAs' bytes complete on the leader's barrier; only the leader arms it
                                 if (mma_leader) mbar_expect_tx(fb, 2u * (uint32_t)stage_bytes);
-                                tma2_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                                tma2_load_4d(sa, ma, fb, c0, w0 + dw, h0 + dh, b0);
                                 tma2_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0 + (int)crank * (a.BN / 2));
                             } else {
                                 mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                                tma_load_4d(sa, &map_a, fb, c0, w0 + dw, h0 + dh, b0);
+                                tma_load_4d(sa, ma, fb, c0, w0 + dw, h0 + dh, b0);
                                 tma_load_2d(sa + A_STAGE_BYTES, &map_b, fb, it * TBK, n0);
                             }
                         }
@@ -592,8 +596,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int n = n0 + col;
                     if (n >= a.Cout) continue;
                     const float2 p0 = gn_stage[0][col], p1 = gn_stage[1][col], p2 = gn_stage[2][col], p3 = gn_stage[3][col];
-                    reinterpret_cast<float2*>(a.gn_partial)[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
-                        make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
+                    float2* gp = reinterpret_cast<float2*>(a.gn_partial);
+                    if (a.HW >= TBM) {
+                        gp[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
+                            make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
+                    } else if (a.HW == 64) {
+                        // the tile holds two whole 8x8 images (two row quarters each): one slot per image
+                        gp[(size_t)bimg * a.Cout + n] = make_float2(p0.x + p1.x, p0.y + p1.y);
+                        if ((bimg + 1) * a.HW < a.M) gp[(size_t)(bimg + 1) * a.Cout + n] = make_float2(p2.x + p3.x, p2.y + p3.y);
+                    } else {                                     // HW == 32: one image per row quarter
+                        const float2 pq[4] = {p0, p1, p2, p3};
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4)
+                            if ((bimg + w4) * a.HW < a.M) gp[(size_t)(bimg + w4) * a.Cout + n] = pq[w4];
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // staging is reused by the next item
             }
@@ -787,7 +803,8 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
     if (!p.ok || (Cout & 3) != 0 || p.BN > 192) return 0;
     if (p.splitk > 1) return splitk_reduce_slots(H * W);  // the split-K reduce emits one slot per 16 rows
     const int HW = H * W;
-    return (HW % TBM == 0) ? HW / TBM : 0;               // a 128-pixel tile must stay inside one image
+    if (HW % TBM == 0) return HW / TBM;                  // tiles inside one image: one slot per tile
+    return (HW == 64 || HW == 32) ? 1 : 0;               // tiles of whole images aligned to the epilogue's row quarters
 }
 
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats) {
@@ -800,7 +817,10 @@ bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, si
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H,
                    int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
-                   cudaStream_t st, int y_half) {
+                   cudaStream_t st, int y_half, const float* x2, int x2_pitch, int Cin1) {
+    // x2 != NULL: input channels [0, Cin1) are read from x, [Cin1, Cin) from x2 (torch.cat never materialised)
+    if (x2 != nullptr && (Cin1 <= 0 || Cin1 >= Cin || Cin1 % TBK != 0 || (x2_pitch & 3) != 0 || !aligned16(x2)))
+        return AFLDM_E_NOKERNEL;
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
     if (y_half && (!p.ok || p.splitk > 1 || residual != nullptr || gn_partial != nullptr || (Cout & 7) != 0 ||
                    (y_pitch & 7) != 0 || !aligned16(y) || (bias != nullptr && !aligned16(bias)) ||
@@ -814,17 +834,21 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     if (p.splitk > 1 && (workspace == nullptr || workspace_floats < (size_t)p.splitk * p.M * Cout))
         return AFLDM_E_WORKSPACE;
 
-    CUtensorMap map_a, map_b;
-    {
-        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)x_pitch * 4, (cuuint64_t)x_pitch * 4 * W,
-                                       (cuuint64_t)x_pitch * 4 * W * H};
+    CUtensorMap map_a, map_a2, map_b;
+    auto encode_a = [&](CUtensorMap* m, const float* src, int pitch, int channels) {
+        const cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * W, (cuuint64_t)pitch * 4 * W * H};
         const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)(p.halo ? p.BH + 2 : p.BH), (cuuint32_t)p.BB};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return AFLDM_E_NOKERNEL;
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(src), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!encode_a(&map_a, x, x_pitch, x2 != nullptr ? Cin1 : Cin)) return AFLDM_E_NOKERNEL;
+    if (x2 != nullptr) {
+        if (!encode_a(&map_a2, x2, x2_pitch, Cin - Cin1)) return AFLDM_E_NOKERNEL;
+    } else {
+        map_a2 = map_a;
     }
     {
         const cuuint64_t K = (cuuint64_t)ks * ks * Cin;
@@ -861,6 +885,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.gn_partial = (p.splitk > 1) ? nullptr : gn_partial;
     a.gn_slots = gn_slots;
     a.y_half = y_half;
+    a.cin1_chunks = x2 != nullptr ? Cin1 / TBK : Cin / TBK;
     a.vec_ok = ((Cout & 3) == 0) && ((y_pitch & 3) == 0) && (y_half || aligned16(y)) && (bias == nullptr || aligned16(bias)) &&
                (row_add == nullptr || (((row_add_pitch & 3) == 0) && aligned16(row_add))) &&
                (residual == nullptr || (((res_pitch & 3) == 0) && aligned16(residual)));
@@ -880,12 +905,12 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (p.halo) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_b, a);
-        else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_b, a);
+        if (p.halo) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_a2, map_b, a);
+        else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_a2, map_b, a);
     } else if (p.halo) {
-        launch_k(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
+        launch_k(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
     } else {
-        launch_k(conv_tc_kernel<false, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_b, a);
+        launch_k(conv_tc_kernel<false, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
     }
     int launches = 1;
     if (p.splitk > 1) {

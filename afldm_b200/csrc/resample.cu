@@ -102,12 +102,25 @@ struct Affine {
     float eps;
     double inv_n;         // 1 / (HW * channels per group), from the host: no fp64 division in the prologue
     float2* gn_out;       // MODE_DOWN2 only: [B][1][C] (sum, sum of squares) of every output plane | NULL
+    const float* x2;      // second input source: channels [xCa, C) are read from x2 (pixel pitch C - xCa), channels
+    int xCa;              // [0, xCa) from x (pixel pitch xCa) - a skip-connection concat that is never materialised
 };
 
 // One warp per GroupNorm group touched by this CTA's CG channels (at most CG of them): the partial sums are added
 // in fp32 (they are fp32 sums over <= 128 pixels already), only the final E[x^2] - mean^2 is formed in fp64.
 // (The first version ran a full fp64 reduction per CHANNEL in every CTA and lost 5 us per call to the separate
 // finalize kernel; this one adds ~1 us of latency to the first wave of CTAs and removes a 3 us launch.)
+// Input source of the channel group that starts at c0: (base pointer incl. channel offset, pixel pitch).
+struct XSrc {
+    const float* p;
+    int pitch;
+};
+__device__ __forceinline__ XSrc x_source(const float* x, int C, const Affine& af, int c0) {
+    if (af.x2 == nullptr) return {x + c0, C};
+    if (c0 < af.xCa) return {x + c0, af.xCa};
+    return {af.x2 + (c0 - af.xCa), C - af.xCa};
+}
+
 template <int CG>
 __device__ __forceinline__ void gn_prologue(const Affine& af, int b, int c0, int C, float* s_sc, float* s_sh) {
     __shared__ float s_mean[CG], s_rstd[CG];
@@ -194,10 +207,11 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
                 sc = af.scale[(size_t)b * C + c0 + c];
                 sh = af.shift[(size_t)b * C + c0 + c];
             }
-            const float* xp = x + ((size_t)(b * N + i) * N) * C + c0 + c;
+            const XSrc xs = x_source(x, C, af, c0);
+            const float* xp = xs.p + ((size_t)(b * N + i) * N) * xs.pitch + c;
             float xr[N], od[N];
 #pragma unroll
-            for (int j = 0; j < N; ++j) xr[j] = fmaf(xp[(size_t)j * C], sc, sh);
+            for (int j = 0; j < N; ++j) xr[j] = fmaf(xp[(size_t)j * xs.pitch], sc, sh);
             up_odd<N>(xr, od);
             float* row = tile + i * PITCH + c;
 #pragma unroll
@@ -366,9 +380,10 @@ resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C
                         sc = af.scale[(size_t)b * C + c0 + c];
                         sh = af.shift[(size_t)b * C + c0 + c];
                     }
-                    const float* xp = x + ((size_t)(b * N + line) * N) * C + c0 + c;
+                    const XSrc xs = x_source(x, C, af, c0);
+                    const float* xp = xs.p + ((size_t)(b * N + line) * N) * xs.pitch + c;
 #pragma unroll
-                    for (int j = 0; j < N; ++j) xr[j] = fmaf(xp[(size_t)j * C], sc, sh);
+                    for (int j = 0; j < N; ++j) xr[j] = fmaf(xp[(size_t)j * xs.pitch], sc, sh);
                 } else {
 #pragma unroll
                     for (int i = 0; i < N; ++i) xr[i] = tile[i * PITCH + line * CG + c];
@@ -566,10 +581,11 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
 
     // ---- stage: x[b][:, :, c0 .. c0 + 8) -> the even columns of T, 2 x 16 B per pixel with cp.async, all in
     // flight at once (one thread per half pixel), so that no MMA chain below waits on a global load.
-    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    const XSrc xs = x_source(x, C, af, c0);
+    if ((xs.pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(xs.p) & 15u) == 0) {
         for (int idx = threadIdx.x; idx < N * N * 2; idx += FM_THREADS) {
             const int half = idx & 1, pix = idx >> 1, i = pix / N, j = pix - i * N;
-            const float* src = x + ((size_t)(b * N + i) * N + j) * C + c0 + 4 * half;
+            const float* src = xs.p + ((size_t)(b * N + i) * N + j) * xs.pitch + 4 * half;
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(T + tix<N>(i, 2 * j) + 4 * half);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
@@ -578,7 +594,7 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
     } else {
         for (int idx = threadIdx.x; idx < N * N * FM_CG; idx += FM_THREADS) {
             const int c = idx & 7, pix = idx >> 3, i = pix / N, j = pix - i * N;
-            T[tix<N>(i, 2 * j) + c] = x[((size_t)(b * N + i) * N + j) * C + c0 + c];
+            T[tix<N>(i, 2 * j) + c] = xs.p[((size_t)(b * N + i) * N + j) * xs.pitch + c];
         }
     }
     __syncthreads();
@@ -817,4 +833,30 @@ extern "C" int afldm_lpf_down2_gn_f32(const float* x, float* y, int B, int H, in
     Affine af = plain_affine(nullptr, nullptr);
     af.gn_out = reinterpret_cast<float2*>(gn_partial);
     return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, as_stream(stream));
+}
+
+extern "C" int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, float* y, int B, int H, int W, int Ca,
+                                             int Cb, int act, const float* partial_a, int slots_a,
+                                             const float* partial_b, int slots_b, int groups, float eps,
+                                             const float* gamma, const float* beta, afldm_stream_t stream) {
+    const int C = Ca + Cb;
+    if (xa == nullptr || xb == nullptr || y == nullptr || partial_a == nullptr || partial_b == nullptr) return AFLDM_E_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || Ca <= 0 || Cb <= 0 || slots_a <= 0 || slots_b <= 0 || groups <= 0) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
+    if (C % groups != 0 || H != W) return AFLDM_E_SHAPE;
+    if (H > 32) return AFLDM_E_NOKERNEL;
+    // a channel group of one CTA (8 / 32 channels) must not straddle the two sources
+    const int cg = (H >= 16 && fact_mma_enabled()) ? FM_CG : (H == 32 ? 8 : (H == 16 ? 16 : 32));
+    if (Ca % cg != 0 || Cb % cg != 0) return AFLDM_E_NOKERNEL;
+    Affine af{};
+    af.pa = reinterpret_cast<const float2*>(partial_a);
+    af.pb = reinterpret_cast<const float2*>(partial_b);
+    af.gamma = gamma; af.beta = beta;
+    af.slots_a = slots_a; af.Ca = Ca; af.slots_b = slots_b; af.Cb = Cb;
+    af.groups = groups; af.HW = H * W; af.eps = eps;
+    af.inv_n = 1.0 / ((double)(H * W) * (double)(C / groups));
+    af.x2 = xb; af.xCa = Ca;
+    cudaStream_t st = as_stream(stream);
+    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(xa, y, B, H, C, af, st);
+    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(xa, y, B, H, C, af, st);
 }

@@ -46,18 +46,38 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
 
     def forward(self, input_tensor: torch.Tensor, temb: Optional[torch.Tensor] = None,
-                temb_proj: Optional[torch.Tensor] = None, *args, **kwargs) -> torch.Tensor:
+                temb_proj: Optional[torch.Tensor] = None, *args, skip: Optional[torch.Tensor] = None,
+                **kwargs) -> torch.Tensor:
         """``temb`` [B, temb_channels]; ``temb_proj`` = precomputed time_emb_proj(act(temb)) [B, Cout]
-        (the UNet batches these for all its resnets into one launch)."""
+        (the UNet batches these for all its resnets into one launch).  ``skip``: the block input is
+        ``torch.cat([input_tensor, skip], dim=1)`` (up blocks); when both consumers of the concat (norm1 + filtered
+        activation, conv_shortcut) can read the two sources directly it is never materialised."""
         x = ops.nhwc(input_tensor)
         if temb_proj is None and temb is not None and self.time_emb_proj is not None:
             temb_proj = ops.linear_rows(temb.contiguous(), self.time_emb_proj.weight, self.time_emb_proj.bias,
                                         act_in="silu")
         w1, b1, k1 = conv_params(self.conv1)
-        h = ops.conv2d(norm_act(x, self.norm1, self.nonlinearity), w1, b1, k1, row_add=temb_proj, gn_stats=True)
+        act1, sc = None, None
+        if skip is not None:
+            xs = ops.nhwc(skip)
+            if isinstance(self.nonlinearity, WarpedNonlinearity) and self.conv_shortcut is not None:
+                n1 = self.norm1
+                act1 = ops.filtered_act_groupnorm_cat(x, xs, n1.num_groups, n1.eps, n1.weight, n1.bias,
+                                                      act=self.nonlinearity.act)
+                if act1 is not None:
+                    ws, bs, ks = conv_params(self.conv_shortcut)
+                    sc = ops.conv2d_cat(x, xs, ws, bs, ks)
+            if act1 is None or sc is None:
+                x = ops.concat_channels(x, xs)
+                act1 = None
+        if act1 is None:
+            act1 = norm_act(x, self.norm1, self.nonlinearity)
+        h = ops.conv2d(act1, w1, b1, k1, row_add=temb_proj, gn_stats=True)
         a = norm_act(h, self.norm2, self.nonlinearity)
         w2, b2, k2 = conv_params(self.conv2)
-        if self.conv_shortcut is not None:
+        if sc is not None:
+            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc, gn_stats=True)
+        elif self.conv_shortcut is not None:
             ws, bs, ks = conv_params(self.conv_shortcut)
             sc = ops.conv2d(x, ws, bs, ks)
             out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc, gn_stats=True)
@@ -253,8 +273,7 @@ class UpBlock2D(nn.Module):
         skips = list(res_hidden_states_tuple)
         for i, resnet in enumerate(self.resnets):
             skip = skips.pop()
-            cat = ops.nchw_view(ops.concat_channels(ops.nhwc(hidden_states), ops.nhwc(skip)))
-            hidden_states = resnet(cat, temb, None if temb_projs is None else temb_projs[i])
+            hidden_states = resnet(hidden_states, temb, None if temb_projs is None else temb_projs[i], skip=skip)
             if self.attentions is not None:
                 hidden_states = self.attentions[i](hidden_states)
         if self.upsamplers is not None:

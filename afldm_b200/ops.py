@@ -149,6 +149,79 @@ def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: O
     return out
 
 
+FUSE_CONCAT = os.environ.get("AFLDM_FUSE_CONCAT", "1") == "1"
+
+
+def filtered_act_groupnorm_cat(a: torch.Tensor, b: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
+                               beta: Optional[torch.Tensor], act: str = "silu") -> Optional[torch.Tensor]:
+    """act-filtered GroupNorm(torch.cat([a, b], channels)) on NHWC a, b WITHOUT materialising the concat (norm1 of an
+    up-block resnet).  Needs the GroupNorm partial sums of both producers; returns None when this form does not
+    apply (missing sums, planes > 32, channel groups straddling the sources) - the caller then concatenates."""
+    ga, gb = getattr(a, "_afldm_gn", None), getattr(b, "_afldm_gn", None)
+    if not (FUSE_CONCAT and FUSE_GN_PROLOGUE) or ga is None or gb is None:
+        return None
+    _chk(a, "a")
+    _chk(b, "b")
+    bsz, h, w, ca = a.shape
+    cb = b.shape[-1]
+    if b.shape[:-1] != a.shape[:-1] or h != w or h > 32 or ga[2] != ca or gb[2] != cb:
+        return None
+    out = torch.empty((bsz, h, w, ca + cb), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+
+    def call():
+        return L.afldm_filtered_act_gn_cat_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), bsz, h, w, ca, cb, ACT[act],
+                                               ga[0].data_ptr(), ga[1], gb[0].data_ptr(), gb[1], groups, float(eps),
+                                               _ptr(gamma), _ptr(beta), _stream())
+
+    code = call()
+    if code == -3:
+        return None
+    _lib.check(code, "filtered_act_gn_cat")
+    if _recorder is not None:
+        _recorder.append(("filtered_act", dict(B=bsz, N=h, C=ca + cb, elems=out.numel(), fused_gn=1, cat=1), call,
+                          (a, b, out, ga[0], gb[0], gamma, beta)))
+    return out
+
+
+def conv2d_cat(a: torch.Tensor, b: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
+               gn_stats: bool = False) -> Optional[torch.Tensor]:
+    """conv2d(torch.cat([a, b], channels)) on the tensor-core path without materialising the concat (conv_shortcut of
+    an up-block resnet).  None when unavailable (exact-fp32 class, shapes outside the tcgen05 family)."""
+    if not FUSE_CONCAT or _default_conv_algo != "tf32":
+        return None
+    _chk(w_packed, "w_packed")
+    bsz, h, w_, ca = a.shape
+    cb = b.shape[-1]
+    cout = w_packed.shape[0]
+    if b.shape[:-1] != a.shape[:-1] or w_packed.shape[-1] != ca + cb:
+        return None
+    pa, pb = _pitch(a), _pitch(b)
+    out = torch.empty((bsz, h, w_, cout), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    need = L.afldm_conv2d_workspace_floats(bsz, h, w_, ca + cb, cout, ksize, 1)
+    ws = scratch(a.device, need) if need else None
+    slots = L.afldm_conv2d_gn_slots(bsz, h, w_, ca + cb, cout, ksize, 1) if gn_stats else 0
+    gn = torch.empty((bsz, slots, cout, 2), dtype=torch.float32, device=a.device) if slots else None
+
+    def call():
+        return L.afldm_conv2d_cat_f32(a.data_ptr(), pa, ca, b.data_ptr(), pb, cb, w_packed.data_ptr(), _ptr(bias), None, 0,
+                                      None, 0, out.data_ptr(), cout, bsz, h, w_, cout, ksize, _ptr(ws), need, _ptr(gn),
+                                      _stream())
+
+    code = call()
+    if code == -3:
+        return None
+    _lib.check(code, "conv2d_cat")
+    if _recorder is not None:
+        _recorder.append(("conv2d_tf32", dict(B=bsz, H=h, W=w_, Cin=ca + cb, Cout=cout, k=ksize, cat=1,
+                                              flops=2.0 * bsz * h * w_ * cout * (ca + cb) * ksize * ksize), call,
+                          (a, b, w_packed, bias, out, ws, gn)))
+    if gn is not None:
+        out._afldm_gn = (gn, slots, cout)
+    return out
+
+
 def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
                            beta: Optional[torch.Tensor], act: str = "silu") -> torch.Tensor:
     """act-filtered GroupNorm(x) on NHWC x: statistics pass (or finalize of the producer's partial sums) +

@@ -81,6 +81,13 @@ AFLDM_API int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H, 
                                         const float* partial_a, int slots_a, int Ca, const float* partial_b,
                                         int slots_b, int Cb, int groups, float eps, const float* gamma,
                                         const float* beta, afldm_stream_t stream);
+/* The same for the input torch.cat([xa, xb], dim=1) of an up-block resnet WITHOUT materialising the concat:
+ * channels [0,Ca) are read from xa (NHWC, pitch Ca), [Ca,Ca+Cb) from xb (pitch Cb); y is the dense NHWC result
+ * with Ca+Cb channels.  AFLDM_E_NOKERNEL when a CTA's channel group would straddle the two sources. */
+AFLDM_API int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, float* y, int B, int H, int W, int Ca,
+                                  int Cb, int act, const float* partial_a, int slots_a,
+                                  const float* partial_b, int slots_b, int groups, float eps,
+                                  const float* gamma, const float* beta, afldm_stream_t stream);
 
 /* UpsampleRFFT(up=2).forward (afldm/af_libs/ideal_lpf.py:148-158), optional affine on load:
  * x NHWC [B,H,W,C] -> y NHWC [B,2H,2W,C]. */
@@ -157,6 +164,16 @@ AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, cons
                      float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
                      int algo, float* workspace, size_t workspace_floats, float* gn_partial,
                      afldm_stream_t stream);
+
+/* afldm_conv2d_f32 (tensor-core path) on the input torch.cat([xa, xb], dim=1) without materialising it: input
+ * channels [0,Ca) come from xa, [Ca,Ca+Cb) from xb (two TMA tensor maps, chosen per 32-channel chunk); w is packed
+ * over Ca+Cb input channels.  The conv_shortcut of an up-block resnet.  AFLDM_E_NOKERNEL when Ca % 32 != 0 or the
+ * shape is outside the tcgen05 family (callers then concatenate and use afldm_conv2d_f32). */
+AFLDM_API int afldm_conv2d_cat_f32(const float* xa, int xa_pitch, int Ca, const float* xb, int xb_pitch, int Cb,
+                         const float* w, const float* bias, const float* row_add, int row_add_pitch,
+                         const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,
+                         int Cout, int ksize, float* workspace, size_t workspace_floats, float* gn_partial,
+                         afldm_stream_t stream);
 
 /* The tensor-core convolution with an fp16 output (y: IEEE binary16, row pitch y_pitch halves, 8-byte aligned rows):
  * y = fp16(conv(x) + bias).  Used for the fused to_q | to_k | to_v projection in front of afldm_attention_f16.

@@ -98,7 +98,8 @@ def test_tcgen05_split_k_is_deterministic():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("b,h,cin,cout,k", [(2, 32, 64, 192, 3), (3, 16, 128, 96, 1), (4, 8, 384, 384, 3), (16, 2, 768, 768, 3)])
+@pytest.mark.parametrize("b,h,cin,cout,k", [(2, 32, 64, 192, 3), (3, 16, 128, 96, 1), (4, 8, 384, 384, 3), (16, 2, 768, 768, 3),
+                                          (16, 8, 384, 384, 1), (3, 8, 384, 384, 1), (16, 8, 768, 384, 1)])
 def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
     """GroupNorm scale/shift finalised from the partial sums the conv epilogue (or the split-K reduce)
     emits == the standalone statistics pass over the conv output."""
@@ -152,3 +153,33 @@ def test_conv_epilogue_groupnorm_partials(b, h, cin, cout, k):
     if h <= 32:
         torch.testing.assert_close(ops.filtered_act_groupnorm(cat, 32, 1e-5, g2, b2), ops.filtered_act(cat, sr, tr),
                                    rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("b,h,ca,cb,cout", [(16, 32, 192, 192, 192), (4, 16, 384, 192, 384), (16, 8, 768, 384, 384),
+                                              (16, 4, 768, 768, 768), (16, 2, 768, 768, 768), (2, 32, 192, 384, 192)])
+def test_unmaterialised_concat_consumers(b, h, ca, cb, cout):
+    """norm1 + filtered activation and conv_shortcut of an up-block resnet reading torch.cat([a, b]) from its two
+    sources (two tensor maps / per-CTA source select) == the same ops on the materialised concat."""
+    x = nhwc(randn(b, 64, h, h, seed=1))
+    wa = ops.pack_conv_weight(randn(ca, 64, 3, 3, seed=2) * 0.05)
+    wb = ops.pack_conv_weight(randn(cb, 64, 3, 3, seed=3) * 0.05)
+    a = ops.conv2d(x, wa, randn(ca, seed=4), 3, algo="tf32", gn_stats=True)
+    bb = ops.conv2d(x, wb, randn(cb, seed=5), 3, algo="tf32", gn_stats=True)
+    assert hasattr(a, "_afldm_gn") and hasattr(bb, "_afldm_gn")
+    cat = ops.concat_channels(a, bb)
+    gamma, beta = randn(ca + cb, seed=6) * 0.2 + 1, randn(ca + cb, seed=7) * 0.2
+    prev = ops.default_conv_algo()
+    ops.set_default_conv_algo("tf32")
+    try:
+        f1 = ops.filtered_act_groupnorm_cat(a, bb, 32, 1e-5, gamma, beta)
+        assert f1 is not None
+        f0 = ops.filtered_act_groupnorm(cat, 32, 1e-5, gamma, beta)
+        torch.testing.assert_close(f1, f0, rtol=0, atol=2e-5)
+        ws = ops.pack_conv_weight(randn(cout, ca + cb, 1, 1, seed=8) * 0.03)
+        bs = randn(cout, seed=9)
+        c1 = ops.conv2d_cat(a, bb, ws, bs, 1)
+        assert c1 is not None
+        c0 = ops.conv2d(cat, ws, bs, 1, algo="tf32")
+        torch.testing.assert_close(c1, c0, rtol=0, atol=1e-5)          # same MMAs in the same order
+    finally:
+        ops.set_default_conv_algo(prev)
