@@ -48,6 +48,7 @@ SIGNATURES = {
     "afldm_softmax_rows_f32": (_i, [_p, _ll, _i, _i, _f, _p]),
     "afldm_timestep_embedding_f32": (_i, [_p, _p, _i, _i, _p]),
     "afldm_concat_channels_f32": (_i, [_p, _i, _p, _i, _p, _ll, _p]),
+    "afldm_pad_channels_f32": (_i, [_p, _i, _p, _i, _ll, _p]),
     "afldm_nchw_to_nhwc_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "afldm_nhwc_to_nchw_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "afldm_axpby_f32": (_i, [_p, _p, _p, _f, _f, _ll, _p]),

@@ -153,6 +153,21 @@ concat_kernel(const float4* __restrict__ a, int Ca4, const float4* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------ channel padding
+// y[p][0 .. C) = x[p][0 .. C), y[p][C .. Cp) = 0: brings a narrow NHWC tensor (the 4-channel latents in front of
+// conv_in) to the 32-channel granularity of the tensor-core convolution's TMA boxes.
+__global__ void __launch_bounds__(256)
+pad_channels_kernel(const float* __restrict__ x, int C, float* __restrict__ y, int Cp, long long total) {
+    pdl_trigger();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long p = i / Cp;
+        const int c = (int)(i - p * Cp);
+        y[i] = c < C ? x[p * C + c] : 0.f;
+    }
+}
+
 // ------------------------------------------------------------------ layout transposes
 // in [B][R][S] -> out [B][S][R]  (NCHW->NHWC: R = C, S = HW; NHWC->NCHW: R = HW, S = C)
 __global__ void __launch_bounds__(256)
@@ -335,5 +350,12 @@ extern "C" int afldm_upfirdn2d_f32(const float* x, const float* f, float* y, int
     const int blocks = (int)((total + 255) / 256);
     launch_k(upfirdn2d_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, f, y, H, W, fh, fw, upx, upy, downx, downy, padx0,
                                                            pady0, outH, outW, flip, gain, total);
+    return launched();
+}
+
+extern "C" int afldm_pad_channels_f32(const float* x, int C, float* y, int Cpad, long long pixels, afldm_stream_t stream) {
+    if (x == nullptr || y == nullptr || C <= 0 || Cpad < C || pixels <= 0 || x == y) return AFLDM_E_ARG;
+    const long long total = pixels * Cpad;
+    launch_k(pad_channels_kernel, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), x, C, y, Cpad, total);
     return launched();
 }

@@ -12,7 +12,7 @@ import torch.nn as nn
 from .. import ops
 from ..af_modules.af_blocks import act_name
 from ..configs import Config, FFHQ_UNET
-from ..packing import conv_params, fused_linear_params
+from ..packing import conv_params, conv_params_padded, fused_linear_params
 from .blocks import DownBlock2D, UNetMidBlock2D, UpBlock2D
 
 
@@ -140,8 +140,15 @@ class UNet2DModel(nn.Module):
             projs = self._time_projections(emb)
 
         x = ops.nhwc(sample)
-        w, b, k = conv_params(self.conv_in)
-        h = ops.nchw_view(ops.conv2d(x, w, b, k))
+        cin = x.shape[-1]
+        if ops.default_conv_algo() == "tf32" and cin % 32 != 0:
+            # 4 latent channels -> one zero-padded 32-channel chunk: conv_in on the tensor-core path, which also
+            # emits the GroupNorm partial sums of its output (first resnet's norm1, last up block's skip concat)
+            w, b, k = conv_params_padded(self.conv_in, 32 * ((cin + 31) // 32))
+            h = ops.nchw_view(ops.conv2d(ops.pad_channels(x, w.shape[-1]), w, b, k, gn_stats=True))
+        else:
+            w, b, k = conv_params(self.conv_in)
+            h = ops.nchw_view(ops.conv2d(x, w, b, k))
         main.wait_stream(side)
         skips = (h,)
         pi = 0

@@ -578,6 +578,17 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def pad_channels(x: torch.Tensor, cpad: int) -> torch.Tensor:
+    """NHWC x [B,H,W,C] -> [B,H,W,cpad] with zeros in the new channels."""
+    _chk(x, "x")
+    c = x.shape[-1]
+    y = torch.empty(x.shape[:-1] + (cpad,), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    _run("pad_channels", dict(elems=y.numel()),
+         lambda: L.afldm_pad_channels_f32(x.data_ptr(), c, y.data_ptr(), cpad, x.numel() // c, _stream()), (x, y))
+    return y
+
+
 def axpby(x: torch.Tensor, e: torch.Tensor, cx, ce, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = cx * x + ce * e.  cx/ce floats, or a device tensor ``coef`` of 2 floats passed as cx (ce None)."""
     _chk(x, "x")

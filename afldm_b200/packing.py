@@ -48,3 +48,19 @@ def fused_linear_params(owner: nn.Module, tag: str, layers: Sequence[nn.Module])
         cache = (key, (w, b))
         object.__setattr__(owner, name, cache)
     return cache[1]
+
+
+def conv_params_padded(m: nn.Module, cin_pad: int) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
+    """``conv_params`` with the input channels zero-padded to ``cin_pad`` (conv_in: 4 latent channels -> one 32-channel
+    TMA chunk, so the layer runs on the tensor-core path; the extra channels multiply zero weights)."""
+    key = _key((m.weight, m.bias)) + (cin_pad,)
+    cache = getattr(m, "_afldm_pack_pad", None)
+    if cache is None or cache[0] != key:
+        w = m.weight.detach()
+        co, ci, kh, kw = w.shape
+        wp = torch.zeros((co, cin_pad, kh, kw), dtype=w.dtype, device=w.device)
+        wp[:, :ci] = w
+        bias = None if m.bias is None else m.bias.detach().contiguous()
+        cache = (key, (ops.pack_conv_weight(wp), bias, kh))
+        object.__setattr__(m, "_afldm_pack_pad", cache)
+    return cache[1]

@@ -221,6 +221,9 @@ AFLDM_API int afldm_timestep_embedding_f32(const float* t, float* out, int B, in
 /* torch.cat([a, b], dim=1) on NHWC: y[.., :Ca] = a, y[.., Ca:] = b (UNet up-path skip concat). */
 AFLDM_API int afldm_concat_channels_f32(const float* a, int Ca, const float* b, int Cb, float* y,
                               long long pixels, afldm_stream_t stream);
+/* y[.., :C] = x, y[.., C:Cpad] = 0 on NHWC (pixels = B*H*W): pads the 4-channel latents to the 32-channel box
+ * granularity of the tensor-core convolution, so conv_in runs on tcgen05 (with zero-padded packed weights). */
+AFLDM_API int afldm_pad_channels_f32(const float* x, int C, float* y, int Cpad, long long pixels, afldm_stream_t stream);
 /* NCHW [B,C,H,W] <-> NHWC [B,H,W,C] (pipeline boundary: latents / decoded frames). */
 AFLDM_API int afldm_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream);
 AFLDM_API int afldm_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int HW, afldm_stream_t stream);
