@@ -38,10 +38,11 @@ _SIDE_STREAMS = {}
 
 def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
     """One auxiliary stream per device for work that is independent of the activation path."""
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)      # one per calling stream: parallel branches stay parallel
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx)
     return st
 
 

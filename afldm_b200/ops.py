@@ -73,13 +73,30 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 # ------------------------------------------------------------------------- scratch
 _scratch = {}
+_scratch_slot = 0
+
+
+class scratch_slot:
+    """Context manager: ops issued inside use scratch buffer ``slot`` (one per concurrently running stream)."""
+
+    def __init__(self, slot: int):
+        self.slot = slot
+
+    def __enter__(self):
+        global _scratch_slot
+        self.prev, _scratch_slot = _scratch_slot, self.slot
+
+    def __exit__(self, *exc):
+        global _scratch_slot
+        _scratch_slot = self.prev
 _scratch_retired = []   # outgrown buffers stay alive: captured CUDA graphs may still point at them
 
 
 def scratch(device: torch.device, nfloats: int) -> torch.Tensor:
-    """One grow-only fp32 scratch buffer per device (split-K partials, GroupNorm partials).
-    All ops run on one stream, so consecutive users may share it."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    """One grow-only fp32 scratch buffer per (device, slot) (split-K partials, large-plane intermediates).
+    Ops on one stream run in order, so consecutive users may share it; code that runs concurrently on a second
+    stream (the second half-batch branch of a captured step) selects its own buffer with ``scratch_slot(1)``."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), _scratch_slot)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nfloats:
         if torch.cuda.is_current_stream_capturing():

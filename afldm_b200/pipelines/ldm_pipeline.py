@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Union
 
+import os
+
 import torch
 
 from .. import ops
@@ -48,6 +50,8 @@ class GraphedDenoiser:
         self.t = torch.ones((batch,), dtype=torch.float32, device=dev)
         self.coef = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
         self.eps = None
+        self.branches = 2 if (os.environ.get("AFLDM_BRANCHES", "1") == "2" and batch % 2 == 0 and batch >= 4) else 1
+        self._fork = torch.cuda.Stream(device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
@@ -63,9 +67,23 @@ class GraphedDenoiser:
         self.launches_per_step = ops._lib.launch_count() - n0
 
     def _body(self):
-        eps = self.unet(ops.nchw_view(self.x), self.t, return_dict=False)[0]
-        self.eps = ops.nhwc(eps)
-        ops.axpby(self.x, self.eps, self.coef, None, out=self.x)
+        if self.branches == 2:
+            # two half batches as two parallel branches of the graph: the launch-latency-bound kernels of the
+            # 8x8 ... 2x2 levels (few CTAs each) and the inter-kernel gaps of one branch overlap the other's work
+            h = self.x.shape[0] // 2
+            main = torch.cuda.current_stream(self.x.device)
+            self._fork.wait_stream(main)
+            with torch.cuda.stream(self._fork), ops.scratch_slot(1):
+                self._half(h, self.x.shape[0])
+            self._half(0, h)
+            main.wait_stream(self._fork)
+            return
+        self._half(0, self.x.shape[0])
+
+    def _half(self, lo: int, hi: int):
+        x = self.x[lo:hi]
+        eps = self.unet(ops.nchw_view(x), self.t[lo:hi], return_dict=False)[0]
+        ops.axpby(x, ops.nhwc(eps), self.coef, None, out=x)
 
     def replay(self):
         self.graph.replay()
