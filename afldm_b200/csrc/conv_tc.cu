@@ -113,6 +113,16 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {     // shared::cta -> shared::cluster of `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -188,6 +198,9 @@ struct TcArgs {
     int halo;                       // 3x3 halo mode: one A box {32 ch, BW, BH + 2} per (kw, channel chunk) serves the 3 kh taps
     int y_half;                     // y is fp16 (y_pitch in halves): QKV projections feeding afldm_attention_f16
     int cin1_chunks;                // channel chunks [0, cin1_chunks) come from map_a, the rest from map_a2 (un-materialised concat)
+    int csk;                        // cluster split-K: the `csk` CTAs of a cluster hold the K splits of one tile and reduce them
+                                    // through distributed shared memory (no partials in global memory, no second launch)
+    int csk_seg;                    // rows per GroupNorm slot in that mode: min(128 / csk, H * W)
 };
 
 // One lane of a converged warp (elect.sync); the same lane every time for the full mask.
@@ -246,13 +259,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* const acc_full = empty_bar + MAX_STAGES;       // [2]
     uint64_t* const acc_empty = acc_full + 2;                // [2]
     uint32_t* const tmem_slot_p = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* const csk_tile = reinterpret_cast<float*>(smem_raw + STAGING_BYTES);   // cluster split-K partial tile (aliases the idle ring)
 
     const int total_iters = a.taps * a.cin_chunks;
-    const uint32_t crank = TWO ? cluster_rank() : 0u;
+    const int csk = TWO ? 0 : a.csk;
+    const uint32_t crank = (TWO || csk > 0) ? cluster_rank() : 0u;
     const bool mma_leader = !TWO || crank == 0u;
     // work items of this CTA (pair): first, first + stride, ...
-    const int n_items = (TWO ? a.mtiles / 2 : a.mtiles) * a.ntiles * a.splitk;
-    const int first = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    // cluster split-K: one tile per cluster, the CTA's cluster rank is its K split
+    const int first = csk > 0 ? (int)blockIdx.x / csk : (TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+    const int n_items = csk > 0 ? first + 1 : (TWO ? a.mtiles / 2 : a.mtiles) * a.ntiles * a.splitk;
     const int stride = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -302,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int mi = item % mrow;
         const int r = item / mrow;
         nt = r % a.ntiles;
-        z = r / a.ntiles;
+        z = csk > 0 ? (int)crank : r / a.ntiles;
         mt = TWO ? 2 * mi + (int)crank : mi;
     };
 
@@ -444,7 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
         const int q = warp & 3;
-        const bool split = a.splitk > 1;
+        const bool split = a.splitk > 1 && csk == 0;
         float* stg = epi_stage[q];
         const int cq = lane & 7, rsub = lane >> 3;      // coalesced phase: 8 lanes x float4 per row, 4 rows per pass
         int j = 0;
@@ -462,7 +478,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // accumulator read, with clamped addresses, so the global-load latency hides under the TMEM load and
                 // the staging transpose instead of serialising the eight store passes (K-light 1x1 layers are
                 // epilogue-bound: profiles/r01_epilogue_notes.md).
-                const bool fast = !split && a.vec_ok && !a.y_half;
+                const bool fast = !split && a.vec_ok && !a.y_half && csk == 0;
                 float4 addv[8];
                 if (fast) {
                     const int nc = min(n0 + c + cq * 4, a.Cout - 4);
@@ -494,6 +510,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if constexpr (TWO) mbar_arrive_cluster(smem_u32(&acc_empty[ab]) & PEER_BIT_MASK);
                         else mbar_arrive_local(smem_u32(&acc_empty[ab]));
                     }
+                }
+                if (csk > 0) {
+                    // cluster split-K: the partial tile stays on chip, [128][BN + 4] fp32 behind the staging area
+                    float4* prow = reinterpret_cast<float4*>(csk_tile + (size_t)(q * 32 + lane) * (a.BN + 4) + c);
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (c + 4 * jj < a.BN)
+                            prow[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                                   __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+                    continue;
                 }
                 // each thread owns one accumulator row: park it in the staging tile ...
                 float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
@@ -586,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 __syncwarp();
             }
-            if (a.gn_partial != nullptr) {
+            if (a.gn_partial != nullptr && csk == 0) {
                 // combine the four row quarters (fixed order) and publish one partial per (tile, channel)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int et = threadIdx.x - 64;            // 0..127 over the epilogue warps
@@ -616,9 +642,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
 
+    if (csk > 0) {
+        // ---- cluster split-K reduction.  Every CTA of the cluster has parked its partial 128 x BN tile in its own
+        // shared memory; CTA `crank` now owns rows [crank * R, (crank + 1) * R), R = 128 / csk: it adds the csk
+        // partials of those rows in rank order (deterministic) straight out of the peers' shared memory, applies the
+        // fused epilogue (+bias +temb row +residual), stores y and emits the GroupNorm partial sums.
+        cluster_sync_all();
+        if (warp >= 2) {
+            int mt, nt, z;
+            decode(first, mt, nt, z);
+            const int m0 = mt * TBM, n0 = nt * a.BN;
+            const int et = (int)threadIdx.x - 64, tq = et >> 5, tl = et & 31;
+            const int R = TBM / csk, PP = a.BN + 4, seg = a.csk_seg, nseg = R / seg;
+            const uint32_t local = smem_u32(csk_tile);
+            uint32_t rbase[8];
+#pragma unroll
+            for (int sidx = 0; sidx < 8; ++sidx) rbase[sidx] = map_to_cta(local, (uint32_t)min(sidx, csk - 1));
+            float2* red = reinterpret_cast<float2*>(smem_raw);           // [4 row lanes][<= 4 segments][BN], in the staging area
+            for (int c4 = tl; c4 * 4 < a.BN; c4 += 32) {
+                const int n = n0 + c4 * 4;
+                const bool colok = n < a.Cout;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (colok && a.bias != nullptr) bv = *reinterpret_cast<const float4*>(a.bias + n);
+                for (int sg = 0; sg < nseg; ++sg) {
+                    float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int r = sg * seg + tq; r < (sg + 1) * seg; r += 4) {
+                        const int row = (int)crank * R + r;
+                        const int mm = m0 + row;
+                        const uint32_t off = (uint32_t)((row * PP + c4 * 4) * 4);
+                        float4 v = ld_cluster_f4(rbase[0] + off);
+#pragma unroll
+                        for (int sidx = 1; sidx < 8; ++sidx) {
+                            if (sidx < csk) {
+                                const float4 u = ld_cluster_f4(rbase[sidx] + off);
+                                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                            }
+                        }
+                        if (mm < a.M && colok) {
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            if (a.row_add != nullptr) {
+                                const float4 t = *reinterpret_cast<const float4*>(a.row_add + (size_t)(mm / a.HW) * a.row_add_pitch + n);
+                                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                            }
+                            if (a.residual != nullptr) {
+                                const float4 t = *reinterpret_cast<const float4*>(a.residual + (size_t)mm * a.res_pitch + n);
+                                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                            }
+                            *reinterpret_cast<float4*>(a.y + (size_t)mm * a.y_pitch + n) = v;
+                            gs[0] += v.x; gs[1] += v.y; gs[2] += v.z; gs[3] += v.w;
+                            gq[0] = fmaf(v.x, v.x, gq[0]); gq[1] = fmaf(v.y, v.y, gq[1]);
+                            gq[2] = fmaf(v.z, v.z, gq[2]); gq[3] = fmaf(v.w, v.w, gq[3]);
+                        }
+                    }
+                    if (a.gn_partial != nullptr) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) red[(tq * 4 + sg) * a.BN + c4 * 4 + jj] = make_float2(gs[jj], gq[jj]);
+                    }
+                }
+            }
+            if (a.gn_partial != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int idx = et; idx < nseg * a.BN; idx += 128) {
+                    const int sg = idx / a.BN, col = idx - sg * a.BN;
+                    const int n = n0 + col;
+                    const int mm = m0 + (int)crank * R + sg * seg;          // first row of this GroupNorm slot
+                    if (n >= a.Cout || mm >= a.M) continue;
+                    const float2 p0 = red[(0 * 4 + sg) * a.BN + col], p1 = red[(1 * 4 + sg) * a.BN + col];
+                    const float2 p2 = red[(2 * 4 + sg) * a.BN + col], p3 = red[(3 * 4 + sg) * a.BN + col];
+                    const int bimg = mm / a.HW, slot = (mm - bimg * a.HW) / seg;
+                    reinterpret_cast<float2*>(a.gn_partial)[((size_t)bimg * a.gn_slots + slot) * a.Cout + n] =
+                        make_float2(((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y);
+                }
+            }
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if constexpr (TWO) cluster_sync_all();          // no CTA leaves while its peer may still signal it
+    if (TWO || csk > 0) cluster_sync_all();         // no CTA leaves while a peer may still signal it / read its shared memory
     if (warp == 1) {
         if constexpr (TWO)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
@@ -666,6 +766,7 @@ struct TcPlan {
     int two;                                            // CTA-pair (cta_group::2) mode
     int ctas_per_sm, grid_ctas, nacc, alias_staging;    // persistent grid and TMEM accumulator buffers
     int halo;                                           // 3x3 halo mode (one A box per kw and channel chunk)
+    int csk, csk_seg;                                   // cluster split-K size (0 = off) and rows per GroupNorm slot
     size_t smem_bytes;
 };
 
@@ -770,6 +871,30 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
         p.total_iters = 3 * (Cin / TBK);          // one stage per (kw, channel chunk): 12 MMAs
         p.iters_per_split = p.total_iters;
     }
+    // Cluster split-K: the K splits of a tile form one thread-block cluster (2 / 4 / 8 CTAs) and are reduced through
+    // distributed shared memory by the kernel itself - no partial tiles in global memory, no reduce launch.  The
+    // GroupNorm slots it emits are min(128 / S, H*W) rows each; at most four per CTA slice.
+    // Measured on B200 it LOSES to the separate reduce kernel (271 vs 287 steps/s: the 4x4-level layers take 25 us
+    // instead of 14.5 us as clusters of 8, the 8x8 level is unchanged as clusters of 4), so it is opt-in
+    // (AFLDM_TC_CSK=1) and documented as a negative result in DESIGN.md.
+    static const int allow_csk = getenv("AFLDM_TC_CSK") ? atoi(getenv("AFLDM_TC_CSK")) : 0;
+    p.csk = 0;
+    p.csk_seg = 0;
+    if (allow_csk && p.splitk > 1 && !p.two && !p.halo && (Cout & 3) == 0 && p.BN <= 192) {
+        const int HW = H * W;
+        for (int S = 8; S >= 2; S >>= 1) {
+            if (S > p.splitk && S > 2) continue;               // never more splits than the rule asked for (except 2)
+            const int R = TBM / S, seg = std::min(R, HW);
+            if (R % seg != 0 || HW % seg != 0 || R / seg > 4) continue;
+            const int ips = ceil_div(p.total_iters, S);
+            if (ceil_div(p.total_iters, ips) != S || ips < 2) continue;
+            p.csk = S;
+            p.csk_seg = seg;
+            p.splitk = S;
+            p.iters_per_split = ips;
+            break;
+        }
+    }
     const int tiles2 = p.mtiles * p.ntiles;
     // More CTAs than SMs and a small stage: size the ring so that two CTAs share an SM and one CTA's
     // prologue / epilogue hides behind the other's main loop.
@@ -791,6 +916,17 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     p.stages = std::max(2, std::min(MAX_STAGES, budget / stage_bytes));
     if (force_stages > 0) p.stages = std::max(2, std::min(force_stages, p.stages));
     p.stages = std::min(p.stages, std::max(2, p.iters_per_split * items_per_cta));   // never more than there is to load
+    if (p.csk) {
+        // one tile per cluster; the parked partial tile [128][BN + 4] sits behind the staging area, inside the ring
+        p.grid_ctas = tiles2 * p.csk;
+        p.alias_staging = 1;
+        p.nacc = 1;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.BN) p.tmem_cols <<= 1;
+        const int need = STAGING_BYTES + TBM * (p.BN + 4) * 4;
+        while (p.stages * stage_bytes < need) ++p.stages;
+        if (p.stages > MAX_STAGES) { p.csk = 0; p.ok = false; return p; }
+    }
     p.smem_bytes = (size_t)p.stages * stage_bytes + (p.alias_staging ? 0 : STAGING_BYTES) + BARRIER_BYTES;
     p.ok = true;
     return p;
@@ -801,6 +937,7 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
 int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
     if (!p.ok || (Cout & 3) != 0 || p.BN > 192) return 0;
+    if (p.csk) return (H * W) / p.csk_seg;               // cluster split-K: one slot per csk_seg rows
     if (p.splitk > 1) return splitk_reduce_slots(H * W);  // the split-K reduce emits one slot per 16 rows
     const int HW = H * W;
     if (HW % TBM == 0) return HW / TBM;                  // tiles inside one image: one slot per tile
@@ -810,7 +947,7 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
     if (!p.ok) return false;
-    *floats = p.splitk > 1 ? (size_t)p.splitk * p.M * Cout : 0;
+    *floats = (p.splitk > 1 && !p.csk) ? (size_t)p.splitk * p.M * Cout : 0;
     return true;
 }
 
@@ -831,7 +968,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     if (!p.ok || (x_pitch & 3) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return AFLDM_E_NOKERNEL;
-    if (p.splitk > 1 && (workspace == nullptr || workspace_floats < (size_t)p.splitk * p.M * Cout))
+    if (p.splitk > 1 && !p.csk && (workspace == nullptr || workspace_floats < (size_t)p.splitk * p.M * Cout))
         return AFLDM_E_WORKSPACE;
 
     CUtensorMap map_a, map_a2, map_b;
@@ -882,7 +1019,9 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.iters_per_split = p.iters_per_split;
     a.BN = p.BN; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
     a.W = W; a.H = H; a.BW = p.BW; a.BH = p.BH;
-    a.gn_partial = (p.splitk > 1) ? nullptr : gn_partial;
+    a.gn_partial = (p.splitk > 1 && !p.csk) ? nullptr : gn_partial;
+    a.csk = p.csk;
+    a.csk_seg = p.csk_seg;
     a.gn_slots = gn_slots;
     a.y_half = y_half;
     a.cin1_chunks = x2 != nullptr ? Cin1 / TBK : Cin / TBK;
@@ -892,6 +1031,23 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     a.mtiles = p.mtiles; a.ntiles = p.ntiles; a.splitk = p.splitk; a.nacc = p.nacc;
     a.alias_staging = p.alias_staging;
     dim3 grid(p.grid_ctas, 1, 1);
+    if (p.csk) {
+        if (!a.vec_ok || y_half) return AFLDM_E_NOKERNEL;      // the DSMEM reduction is float4 throughout
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = p.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = p.csk;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_a2, map_b, a);
+        return launched(1);
+    }
     if (p.two) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid;
