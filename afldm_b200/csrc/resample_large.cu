@@ -278,15 +278,27 @@ line_mma_kernel(const LineArgs a) {
 
     uint32_t ah[KS][4], al[KS][4];
     if constexpr (OP == OP_UP || OP == OP_UPACTDOWN) {
-        // load the line (positions 8 nt + 2 t + q), keep the even samples: in global memory (UP) or the warp's tile
+        // load the whole line first (positions 8 nt + 2 t + q): all loads in flight at once - the stores below may alias
+        // the input as far as the compiler knows, so interleaving them serialises load -> store -> load
+        float v[KS][4][2];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int idx = 0; idx < 4; ++idx) {
+                const int r = idx & 1, j = 8 * (2 * ks + (idx >> 1)) + 2 * t;
+                v[ks][idx][0] = xin[r][(size_t)j * a.in_pos];
+                v[ks][idx][1] = xin[r][(size_t)(j + 1) * a.in_pos];
+            }
+        }
+        // keep the even samples: in global memory (UP) or the warp's tile
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
             for (int idx = 0; idx < 4; ++idx) {
                 const int r = idx & 1, nt = 2 * ks + (idx >> 1);
                 const int j = 8 * nt + 2 * t;
-                const float v0 = fmaf(xin[r][(size_t)j * a.in_pos], sc[r], sh[r]);
-                const float v1 = fmaf(xin[r][(size_t)(j + 1) * a.in_pos], sc[r], sh[r]);
+                const float v0 = fmaf(v[ks][idx][0], sc[r], sh[r]);
+                const float v1 = fmaf(v[ks][idx][1], sc[r], sh[r]);
                 lm_split(v0, v1, ah[ks][idx], al[ks][idx]);
                 if constexpr (OP == OP_UP) {
                     if (ok[r]) {
@@ -331,19 +343,40 @@ line_mma_kernel(const LineArgs a) {
 #pragma unroll
             for (int idx = 0; idx < 4; ++idx) { ah[ks][idx] = oh[ks][idx]; al[ks][idx] = ol[ks][idx]; }
     } else {
-        // OP_DOWN: the line has 2N samples; odd ones -> A fragments, even ones -> the warp's tile
+        // OP_DOWN: the line has 2N samples; odd ones -> A fragments, even ones -> the warp's tile (two load batches)
+        {
+            float v[KS][4][2];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
+            for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-            for (int idx = 0; idx < 4; ++idx) {
-                const int r = idx & 1, nt = 2 * ks + (idx >> 1);
-                const int j = 8 * nt + 2 * t;
-                const float e0 = xin[r][(size_t)(2 * j) * a.in_pos], o0 = xin[r][(size_t)(2 * j + 1) * a.in_pos];
-                const float e1 = xin[r][(size_t)(2 * j + 2) * a.in_pos], o1 = xin[r][(size_t)(2 * j + 3) * a.in_pos];
-                lm_split(o0, o1, ah[ks][idx], al[ks][idx]);
-                etile[j * LM_EP + g + 8 * r] = e0;
-                etile[(j + 1) * LM_EP + g + 8 * r] = e1;
-            }
+                for (int idx = 0; idx < 4; ++idx) {
+                    const int r = idx & 1, j = 8 * (2 * ks + (idx >> 1)) + 2 * t;
+                    v[ks][idx][0] = xin[r][(size_t)(2 * j + 1) * a.in_pos];
+                    v[ks][idx][1] = xin[r][(size_t)(2 * j + 3) * a.in_pos];
+                }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int idx = 0; idx < 4; ++idx) lm_split(v[ks][idx][0], v[ks][idx][1], ah[ks][idx], al[ks][idx]);
+        }
+        {
+            float v[KS][4][2];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int idx = 0; idx < 4; ++idx) {
+                    const int r = idx & 1, j = 8 * (2 * ks + (idx >> 1)) + 2 * t;
+                    v[ks][idx][0] = xin[r][(size_t)(2 * j) * a.in_pos];
+                    v[ks][idx][1] = xin[r][(size_t)(2 * j + 2) * a.in_pos];
+                }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int idx = 0; idx < 4; ++idx) {
+                    const int r = idx & 1, j = 8 * (2 * ks + (idx >> 1)) + 2 * t;
+                    etile[j * LM_EP + g + 8 * r] = v[ks][idx][0];
+                    etile[(j + 1) * LM_EP + g + 8 * r] = v[ks][idx][1];
+                }
         }
     }
     __syncwarp();

@@ -30,6 +30,8 @@ for _ in range(3):
         ops.attention(qkv[:, :, :192], qkv[:, :, 192:384], qkv[:, :, 384:], 8, algo="tf32")
         qh = qkv.half()
         ops.attention_f16(qh[:, :, :192], qh[:, :, 192:384], qh[:, :, 384:], 8)
+    if which in ("large",):
+        ops.filtered_act(r(4, 128, 128, 256))
     if which in ("all", "lin"):
         ops.linear_rows(r(16, 768), r(14016, 768) * 0.03, r(14016), act_in="silu")
 torch.cuda.synchronize()
