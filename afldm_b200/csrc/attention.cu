@@ -431,7 +431,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // D: head dim (multiple of 8, <= 64); MT: 16-row query tiles per warp.  4 warps, 64 * MT queries per CTA.
 template <int D, int MT>
-__global__ void __launch_bounds__(128, MT == 2 ? 3 : 5)
+__global__ void __launch_bounds__(128, MT == 2 ? 4 : 5)
 attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __restrict__ k,
                      const __half* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                      int Bkv_rep, int Nq, int Nk, float scale_log2e) {
