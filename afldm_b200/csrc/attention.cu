@@ -436,7 +436,6 @@ attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __
                      const __half* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                      int Bkv_rep, int Nq, int Nk, float scale_log2e) {
     pdl_trigger();
-    pdl_wait();
     constexpr int KT = 64;                       // keys per tile
     constexpr int DP = (D + 15) / 16 * 16;       // head dim padded to the MMA k (zero columns)
     constexpr int KS = DP / 16;                  // k-steps of Q.K^T
@@ -457,6 +456,7 @@ attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __
         const int row = idx / ((PH - D) / 8), c8 = idx - row * ((PH - D) / 8);
         *reinterpret_cast<uint4*>(att_h + row * PH + D + 8 * c8) = make_uint4(0u, 0u, 0u, 0u);
     }
+    pdl_wait();                                  // q / k / v come from the previous kernel (QKV projection)
 
     const __half* kbase = k + ((size_t)bkv * Nk) * kv_pitch + head * D;
     const __half* vbase = v + ((size_t)bkv * Nk) * kv_pitch + head * D;

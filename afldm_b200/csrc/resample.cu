@@ -556,19 +556,20 @@ template <int N, int ACT>
 __global__ void __launch_bounds__(FM_THREADS, 2)
 fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const Affine af) {
     pdl_trigger();
-    pdl_wait();
     extern __shared__ float T[];
     __shared__ float s_sc[FM_CG], s_sh[FM_CG];
     const int b = blockIdx.y, c0 = blockIdx.x * FM_CG;
-    if (af.pa != nullptr) gn_prologue<FM_CG>(af, b, c0, C, s_sc, s_sh);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     constexpr int NT = N / 8;
     constexpr int NWARPS = FM_THREADS / 32;
 
+    // filter fragments depend on nothing the previous kernel wrote: built before the dependency wait, under its tail
     CircB<N> fu, fd;
     make_circ<N, false>(fu, g, t);
     make_circ<N, true>(fd, g, t);
+    pdl_wait();
+    if (af.pa != nullptr) gn_prologue<FM_CG>(af, b, c0, C, s_sc, s_sh);
 
     float sc = 1.f, sh = 0.f;
     if (af.pa != nullptr) {

@@ -245,7 +245,6 @@ template <int N, int OP, int ACT>
 __global__ void __launch_bounds__(32 * LM_WARPS)
 line_mma_kernel(const LineArgs a) {
     pdl_trigger();
-    pdl_wait();
     extern __shared__ __align__(16) unsigned char lm_smem[];
     uint4* fu = reinterpret_cast<uint4*>(lm_smem);                       // [(N/8)][32]
     uint4* fd = fu + (N / 8) * 32;
@@ -253,6 +252,7 @@ line_mma_kernel(const LineArgs a) {
     if constexpr (OP != OP_DOWN) lm_fill_filter<N, false>(fu, threadIdx.x, blockDim.x);
     if constexpr (OP != OP_UP) lm_fill_filter<N, true>(fd, threadIdx.x, blockDim.x);
     __syncthreads();
+    pdl_wait();                                      // the filter tables above do not depend on the previous kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int mt = blockIdx.y * LM_WARPS + warp;
     const int ch = blockIdx.x * 8 + g;
