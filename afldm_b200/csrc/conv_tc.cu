@@ -236,6 +236,7 @@ template <bool TWO, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
+    pdl_trigger();                                           // dependents may start their own prologue right away
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static smem: the ring starts 1024-aligned
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t smem_base = smem_u32(smem_raw);
@@ -308,7 +309,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot_p;
     // Everything above touched only this CTA's shared / tensor memory: it may overlap the tail of the
     // previous kernel on the stream.  From here on global memory is read.
-    pdl_trigger();
     pdl_wait();
 
     // item -> (M tile, N tile, K split).  M fastest: neighbouring CTAs (and the two CTAs sharing an SM) work on
