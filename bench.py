@@ -274,6 +274,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     ops.set_default_conv_algo(args.conv_algo)
