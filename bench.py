@@ -274,8 +274,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: ONE JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator is created: route fd 1 to stderr around the
+        # (eager, device_id=) initialisation and the first collective so that stdout carries ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     ops.set_default_conv_algo(args.conv_algo)
     pipe = MyLDMPipeline.from_config(seed=0, with_vae=False).to(dev)
