@@ -368,6 +368,22 @@ def test_linear_rows_and_timestep_embedding():
                                F.silu(F.linear(x20, w[:, :256], bias)), rtol=0, atol=2e-5)
 
 
+def test_pad_channels_and_tensor_core_conv_in():
+    """conv_in on the tensor-core path: latents zero-padded to one 32-channel chunk + zero-padded weights == the
+    exact-fp32 4-channel convolution within the TF32 bound."""
+    x = randn(16, 32, 32, 4, seed=1)
+    xp = ops.pad_channels(x, 32)
+    assert xp.shape == (16, 32, 32, 32) and torch.equal(xp[..., :4], x) and xp[..., 4:].abs().max() == 0
+    w = randn(192, 4, 3, 3, seed=2) * 0.2
+    wp = torch.zeros(192, 32, 3, 3, device=DEV)
+    wp[:, :4] = w
+    bias = randn(192, seed=3)
+    got = ops.conv2d(xp, ops.pack_conv_weight(wp), bias, 3, algo="tf32", gn_stats=True)
+    assert hasattr(got, "_afldm_gn")
+    want = ops.conv2d(x, ops.pack_conv_weight(w), bias, 3, algo="simt")
+    assert (got - want).abs().max().item() < 8e-3
+
+
 def test_layout_concat_axpby_softmax():
     x = randn(3, 20, 5, 7, seed=1)
     y = ops.nhwc(x)
