@@ -169,7 +169,9 @@ def test_unmaterialised_concat_consumers(b, h, ca, cb, cout):
     cat = ops.concat_channels(a, bb)
     gamma, beta = randn(ca + cb, seed=6) * 0.2 + 1, randn(ca + cb, seed=7) * 0.2
     prev = ops.default_conv_algo()
+    flags = (ops.FUSE_GN_PROLOGUE, ops.FUSE_CONCAT)
     ops.set_default_conv_algo("tf32")
+    ops.FUSE_GN_PROLOGUE, ops.FUSE_CONCAT = True, True          # independent of the AFLDM_FUSE_* environment switches
     try:
         f1 = ops.filtered_act_groupnorm_cat(a, bb, 32, 1e-5, gamma, beta)
         assert f1 is not None
@@ -183,3 +185,4 @@ def test_unmaterialised_concat_consumers(b, h, ca, cb, cout):
         torch.testing.assert_close(c1, c0, rtol=0, atol=1e-5)          # same MMAs in the same order
     finally:
         ops.set_default_conv_algo(prev)
+        ops.FUSE_GN_PROLOGUE, ops.FUSE_CONCAT = flags
