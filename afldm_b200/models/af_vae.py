@@ -125,6 +125,18 @@ class AutoencoderKL(nn.Module):
         cfg.update(overrides)
         return cls(**{k: v for k, v in cfg.items() if not k.startswith("_")})
 
+    @classmethod
+    def from_pretrained(cls, path_or_repo: str, subfolder=None, **_unused):
+        """config.json (incl. the alias-free flags of configs/vae/model_afvae.json) + weights of a local directory /
+        cached repo.  ``AutoencoderKL`` loads the plain module (scripts then call ``make_af_vae_from_config``);
+        ``AliasFreeAutoencoderKL`` applies the surgery in its constructor (af_vae.py:8-55)."""
+        from .. import hub
+        return hub.load_model(cls, path_or_repo, subfolder)
+
+    def save_pretrained(self, directory: str, safe_serialization: bool = True):
+        from .. import hub
+        hub.save_model(self, directory, "AutoencoderKL", safe_serialization)
+
     @property
     def dtype(self):
         return self.post_quant_conv.weight.dtype

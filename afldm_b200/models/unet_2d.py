@@ -94,6 +94,17 @@ class UNet2DModel(nn.Module):
         cfg.update(overrides)
         return cls(**{k: v for k, v in cfg.items() if not k.startswith("_")})
 
+    @classmethod
+    def from_pretrained(cls, path_or_repo: str, subfolder=None, **_unused):
+        """diffusers ``UNet2DModel.from_pretrained``: config.json + safetensors of a local directory / cached repo
+        (plain module; the caller applies ``make_af_unet`` as the reference's scripts do)."""
+        from .. import hub
+        return hub.load_model(cls, path_or_repo, subfolder)
+
+    def save_pretrained(self, directory: str, safe_serialization: bool = True):
+        from .. import hub
+        hub.save_model(self, directory, "UNet2DModel", safe_serialization)
+
     @property
     def dtype(self):
         return self.conv_in.weight.dtype

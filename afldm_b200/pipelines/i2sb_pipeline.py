@@ -13,6 +13,8 @@ from .ldm_pipeline import ImagePipelineOutput, MyLDMPipeline
 
 
 class I2SBLDMPipeline(MyLDMPipeline):
+    SCHEDULER_CLS = I2SBScheduler
+
     def __init__(self, vae, unet, scheduler: I2SBScheduler):
         super().__init__(vae, unet, scheduler)
 

@@ -108,6 +108,35 @@ class MyLDMPipeline:
         vae = AliasFreeAutoencoderKL.from_config(vae_config) if with_vae else None
         return cls(vae, unet, DDIMScheduler.from_config(scheduler_config))
 
+    SCHEDULER_CLS = DDIMScheduler
+
+    @classmethod
+    def from_pretrained(cls, path_or_repo: str, **_unused):
+        """``DiffusionPipeline.from_pretrained`` for the diffusers directory layout (unet/, vae/, scheduler/; local path or a
+        repo id present in the local Hugging Face cache).  Like the reference, this returns PLAIN modules: the scripts
+        then call ``make_af_unet(pipe.unet)`` and ``make_af_vae_from_config(pipe.vae)`` (shift_ldm_ffhq.py:165-170)."""
+        import os
+        from .. import hub
+        from ..models.af_vae import AutoencoderKL
+        d = hub.resolve(path_or_repo)
+        unet = UNet2DModel.from_pretrained(d, subfolder="unet")
+        vae = AutoencoderKL.from_pretrained(d, subfolder="vae") if os.path.isdir(os.path.join(d, "vae")) else None
+        return cls(vae, unet, cls.SCHEDULER_CLS.from_pretrained(d, subfolder="scheduler"))
+
+    def save_pretrained(self, directory: str, safe_serialization: bool = True):
+        import json
+        import os
+        os.makedirs(directory, exist_ok=True)
+        index = {"_class_name": type(self).__name__, "_diffusers_version": "0.32.1",
+                 "unet": ["diffusers", "UNet2DModel"], "scheduler": ["diffusers", type(self.scheduler).__name__]}
+        self.unet.save_pretrained(os.path.join(directory, "unet"), safe_serialization)
+        if self.vae is not None:
+            index["vae"] = ["diffusers", "AutoencoderKL"]
+            self.vae.save_pretrained(os.path.join(directory, "vae"), safe_serialization)
+        self.scheduler.save_pretrained(os.path.join(directory, "scheduler"))
+        with open(os.path.join(directory, "model_index.json"), "w") as f:
+            json.dump(index, f, indent=2)
+
     def to(self, device):
         self.unet.to(device)
         if self.vae is not None:

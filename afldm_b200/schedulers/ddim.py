@@ -41,6 +41,15 @@ class DDIMScheduler:
         self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
 
     @classmethod
+    def from_pretrained(cls, path_or_repo: str, subfolder="scheduler", **_unused):
+        from .. import hub
+        return hub.load_scheduler(cls, path_or_repo, subfolder)
+
+    def save_pretrained(self, directory: str):
+        from .. import hub
+        hub.save_scheduler(self, directory, "DDIMScheduler")
+
+    @classmethod
     def from_config(cls, config=FFHQ_DDIM, **overrides):
         cfg = dict(config)
         cfg.update(overrides)

@@ -41,6 +41,15 @@ class I2SBScheduler:
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy())
 
     @classmethod
+    def from_pretrained(cls, path_or_repo: str, subfolder="scheduler", **_unused):
+        from .. import hub
+        return hub.load_scheduler(cls, path_or_repo, subfolder)
+
+    def save_pretrained(self, directory: str):
+        from .. import hub
+        hub.save_scheduler(self, directory, "I2SBScheduler")
+
+    @classmethod
     def from_config(cls, config=FFHQ_DDIM, **overrides):
         cfg = dict(config)
         cfg.update(overrides)
