@@ -33,10 +33,16 @@ def _denoise(unet, sched, state, x, tensor_t):
     return x.contiguous()
 
 
-def test_shift_equivariance_metric_matches_oracle():
+@pytest.mark.parametrize("algo,tol_db,tol_traj", [("simt", 0.05, 1e-3), ("tf32", 0.05, 3e-2)])
+def test_shift_equivariance_metric_matches_oracle(algo, tol_db, tol_traj):
+    """``simt``: exact-fp32 kernels, the masked shift-PSNR equals the oracle's to 0.05 dB.  ``tf32``: the benchmarked
+    class (TF32 convolutions, fp16-operand attention where the projections are un-split, tensor-core filtered
+    activation) against the SAME fp32 oracle: the equivariance metric moves by less than 0.05 dB (measured 0.006 dB:
+    41.129 / 34.094 vs 41.124 / 34.088)."""
     a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-    ops.set_default_conv_algo("simt")
+    prev_algo = ops.default_conv_algo()
+    ops.set_default_conv_algo(algo)
     try:
         torch.manual_seed(0)
         ref = ON.UNet2DModel(**CFG).to(DEV).eval()
@@ -54,7 +60,7 @@ def test_shift_equivariance_metric_matches_oracle():
             st_m.reset()
             base_r = _denoise(ref, ON.DDIMScheduler(), st_r, init, True)
             base_m = _denoise(mine, DDIMScheduler.from_config(), st_m, init, False)
-            torch.testing.assert_close(base_m, base_r, rtol=0, atol=1e-3)
+            torch.testing.assert_close(base_m, base_r, rtol=0, atol=tol_traj)
             st_r.to_load()
             st_m.to_load()
             psnr_r, psnr_m = [], []
@@ -67,8 +73,9 @@ def test_shift_equivariance_metric_matches_oracle():
                 out_m = _denoise(mine, DDIMScheduler.from_config(), st_m, shifted, False)
                 psnr_r.append(float(OS.mask_psnr(out_r, want_r, mask)))
                 psnr_m.append(float(OS.mask_psnr(out_m, want_m, mask)))
-        print("masked shift-PSNR (dB)  oracle:", [round(p, 3) for p in psnr_r], " cuda:", [round(p, 3) for p in psnr_m])
+        print(f"masked shift-PSNR (dB) [{algo}]  oracle:", [round(p, 3) for p in psnr_r], " cuda:", [round(p, 3) for p in psnr_m])
         for pr, pm in zip(psnr_r, psnr_m):
-            assert abs(pr - pm) < 0.05, (psnr_r, psnr_m)
+            assert abs(pr - pm) < tol_db, (psnr_r, psnr_m)
     finally:
+        ops.set_default_conv_algo(prev_algo)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
