@@ -27,13 +27,14 @@ void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const 
                           int HW, float* gn_partial, cudaStream_t st);
 
 // tcgen05 / TMA path.  Returns false (and leaves *floats alone) when the shape is not covered.
-bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats);
+bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats, int x_half = 0);
 // Number of GroupNorm partial-sum slots per image the tensor-core path emits for this shape
 // (gn_partial [B][slots][Cout] float2), 0 when it cannot (shape outside the family, ragged tiles).
-int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks);
+int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks, int x_half = 0);
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,
                    int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
-                   cudaStream_t st, int y_half = 0, const float* x2 = nullptr, int x2_pitch = 0, int Cin1 = 0);
+                   cudaStream_t st, int y_half = 0, const float* x2 = nullptr, int x2_pitch = 0, int Cin1 = 0,
+                   int x_half = 0);   // x_half: x / x2 / w are fp16 (tcgen05.mma.kind::f16), pitches in elements
 
 }  // namespace afldm

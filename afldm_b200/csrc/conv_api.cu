@@ -21,9 +21,10 @@ bool conv_bad_args(const float* x, int x_pitch, const float* w, const float* y, 
 
 extern "C" size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
-    if (algo == AFLDM_CONV_TCGEN05_TF32) {
+    if (algo == AFLDM_CONV_TCGEN05_TF32 || algo == AFLDM_CONV_TCGEN05_F16) {
         size_t need = 0;
-        if (conv_tc_workspace_floats(B, H, W, Cin, Cout, ksize, &need)) return need;
+        if (conv_tc_workspace_floats(B, H, W, Cin, Cout, ksize, &need, algo == AFLDM_CONV_TCGEN05_F16)) return need;
+        if (algo == AFLDM_CONV_TCGEN05_F16) return 0;
         // shape not covered by the tensor-core path: callers fall back to SIMT
     }
     const ConvPlan p = conv_simt_plan(B, H, W, Cin, Cout, ksize);
@@ -32,8 +33,8 @@ extern "C" size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, in
 
 extern "C" int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
-    if (algo != AFLDM_CONV_TCGEN05_TF32) return 0;
-    return conv_tc_gn_slots(B, H, W, Cin, Cout, ksize);
+    if (algo != AFLDM_CONV_TCGEN05_TF32 && algo != AFLDM_CONV_TCGEN05_F16) return 0;
+    return conv_tc_gn_slots(B, H, W, Cin, Cout, ksize, algo == AFLDM_CONV_TCGEN05_F16);
 }
 
 extern "C" int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
@@ -62,6 +63,19 @@ extern "C" int afldm_conv2d_f16out(const float* x, int x_pitch, const float* w, 
         return AFLDM_E_ARG;
     return conv_tc_launch(x, x_pitch, w, bias, nullptr, 0, nullptr, 0, static_cast<float*>(y), y_pitch, B, H, W, Cin, Cout,
                           ksize, nullptr, 0, nullptr, as_stream(stream), 1);
+}
+
+extern "C" int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, const float* bias,
+                                      const float* row_add, int row_add_pitch, const float* residual, int res_pitch,
+                                      float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
+                                      float* workspace, size_t workspace_floats, float* gn_partial,
+                                      afldm_stream_t stream) {
+    const float* xf = static_cast<const float*>(x);
+    const float* wf = static_cast<const float*>(w);
+    if (conv_bad_args(xf, x_pitch, wf, y, y_pitch, row_add, row_add_pitch, residual, res_pitch, B, H, W, Cin, Cout, ksize))
+        return AFLDM_E_ARG;
+    return conv_tc_launch(xf, x_pitch, wf, bias, row_add, row_add_pitch, residual, res_pitch, y, y_pitch, B, H, W, Cin,
+                          Cout, ksize, workspace, workspace_floats, gn_partial, as_stream(stream), 0, nullptr, 0, 0, 1);
 }
 
 extern "C" int afldm_conv2d_cat_f32(const float* xa, int xa_pitch, int Ca, const float* xb, int xb_pitch, int Cb,

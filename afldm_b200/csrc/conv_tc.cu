@@ -33,9 +33,12 @@ namespace afldm {
 namespace {
 
 constexpr int TBM = 128;           // output pixels per tile (UMMA M)
-constexpr int TBK = 32;            // K elements per stage: 32 fp32 = 128 B = one swizzle row
-constexpr int UMMA_K = 8;          // K per tcgen05.mma.kind::tf32
-constexpr int A_STAGE_BYTES = TBM * TBK * 4;   // 16 KB
+constexpr int ROW_BYTES = 128;     // K bytes per stage and tile row = one swizzle row: 32 tf32 or 64 fp16 elements
+constexpr int MMAS_PER_STAGE = 4;  // 32 B of K per tcgen05.mma: K = 8 (kind::tf32) or K = 16 (kind::f16)
+constexpr int A_STAGE_BYTES = TBM * ROW_BYTES;   // 16 KB
+// K elements per stage: fp16 operands (F16) pack twice the K into the same bytes, and kind::f16 retires twice the
+// K per instruction - the same ring, descriptors and byte counts serve both, at half the stages per layer.
+__host__ __device__ constexpr int tbk(bool f16) { return f16 ? 64 : 32; }
 // All shared memory is dynamic: [stage ring | epilogue staging | mbarriers + TMEM slot].  (The kernel is
 // persistent, so the epilogue of one tile overlaps the ring traffic of the next: staging cannot alias the ring.)
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 36 * 4;                 // 4 epilogue warps x 32 rows x (32 + 4) floats
@@ -100,6 +103,24 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uin
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -232,7 +253,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {      // bar:
 // TWO = true: tcgen05.mma.cta_group::2 (M = 256) over a cluster of two CTAs; each CTA stages its own 128 rows
 // of A and BN/2 rows of B (16 KB + BN*64 B per stage instead of 16 KB + BN*128 B): the SM's operand ingest,
 // the measured bound of the main loop, buys up to 2x the FLOPs.
-template <bool TWO, bool HALO>
+template <bool TWO, bool HALO, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                const __grid_constant__ CUtensorMap map_b, const TcArgs a) {
@@ -241,13 +262,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t smem_base = smem_u32(smem_raw);
     if ((smem_base & 1023u) != 0u) __trap();                 // swizzle-128B atoms need 1024 B alignment
-    const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * TBK * 4;
+    constexpr int TBK = tbk(F16);                            // K elements (channels) per stage
+    const int b_stage_bytes = (TWO ? a.BN / 2 : a.BN) * ROW_BYTES;
     // Halo mode (3x3, tile = BH >= 2 whole image rows): a stage holds the box of BH + 2 rows shifted by kw - 1
     // and the three weight tiles of taps (kh, kw), kh = 0..2.  Tap kh reads the SAME box BW rows further down
     // (a multiple of the 1024 B swizzle atom, so only the descriptor start address moves): the SM ingests
     // 3 (BH + 2) / (9 BH) of the activation bytes of the one-box-per-tap scheme - the measured bound of the
     // main loop is operand bytes staged per SM (profiles/r01_conv_notes.md).
-    const int a_bytes = HALO ? (a.BH + 2) * a.BW * TBK * 4 : A_STAGE_BYTES;
+    const int a_bytes = HALO ? (a.BH + 2) * a.BW * ROW_BYTES : A_STAGE_BYTES;
     constexpr int nb = HALO ? 3 : 1;
     const int stage_bytes = a_bytes + nb * b_stage_bytes;
     // layout: [stage ring][epilogue staging 4 x 32 x 36 floats][GroupNorm staging 4 x 192 float2][barriers]
@@ -407,9 +429,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (mma_leader) {
-            // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major both,
+            // instruction descriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10) or F16 (0, 0), K-major both,
             // N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 for the CTA pair)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) |
+            constexpr uint32_t ab_fmt = F16 ? 0u : ((2u << 7) | (2u << 10));
+            const uint32_t idesc = (1u << 4) | ab_fmt | ((uint32_t)(a.BN >> 3) << 17) |
                                    ((uint32_t)((TWO ? 2 * TBM : TBM) >> 4) << 24);
             int s = 0;
             uint32_t ph = 0;
@@ -431,14 +454,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                         for (int kh = 0; kh < nb; ++kh) {
                             // halo mode: tap kh = the same box, BW pixel rows (BW * 128 B) further down
-                            const uint64_t da = make_desc(sa + (HALO ? (uint32_t)(kh * a.BW * TBK * 4) : 0u));
+                            const uint64_t da = make_desc(sa + (HALO ? (uint32_t)(kh * a.BW * ROW_BYTES) : 0u));
                             const uint64_t db = make_desc(sa + (uint32_t)a_bytes + (uint32_t)(kh * b_stage_bytes));
 #pragma unroll
-                            for (int k = 0; k < TBK / UMMA_K; ++k) {
-                                // advance 8 fp32 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+                            for (int k = 0; k < MMAS_PER_STAGE; ++k) {
+                                // advance 8 fp32 / 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
                                 const uint32_t acc = (i | kh | k) != 0 ? 1u : 0u;
-                                if constexpr (TWO) umma2_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
-                                else umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                if constexpr (F16) {
+                                    if constexpr (TWO) umma2_f16(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                    else umma_f16(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                } else {
+                                    if constexpr (TWO) umma2_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                    else umma_tf32(tacc, da + 2 * k, db + 2 * k, idesc, acc);
+                                }
                             }
                         }
                         // frees the stage (in both CTAs of a pair) when these MMAs retire
@@ -770,9 +798,10 @@ struct TcPlan {
     size_t smem_bytes;
 };
 
-TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
+TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks, bool f16 = false) {
     TcPlan p{};
     p.ok = false;
+    const int TBK = tbk(f16);            // channels per 128-byte stage row
     // Cout < 16 (conv_out: C -> 4 / 3) runs as one BN = 16 tile: the weight box rows past Cout are
     // zero-filled by TMA and the epilogue masks them.
     if (Cin % TBK != 0 || (Cout >= 16 && Cout % 16 != 0) || !is_pow2(W) || !is_pow2(H)) return p;
@@ -865,8 +894,8 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
     // 60 KB halo stages leave a 3-deep ring (sweep on B200, profiles/r01_conv_halo_sweep.md: 68.9 vs 63.2 us).
     p.halo = (allow_halo && ks == 3 && p.splitk == 1 && p.BB == 1 && p.BH >= 2 && p.BW >= 8 && p.BW * p.BH == TBM &&
               !(p.two && p.BN >= 192 && allow_halo < 2)) ? 1 : 0;
-    const int b_bytes = (p.two ? p.BN / 2 : p.BN) * TBK * 4;
-    const int stage_bytes = p.halo ? (p.BH + 2) * p.BW * TBK * 4 + 3 * b_bytes : A_STAGE_BYTES + b_bytes;
+    const int b_bytes = (p.two ? p.BN / 2 : p.BN) * ROW_BYTES;
+    const int stage_bytes = p.halo ? (p.BH + 2) * p.BW * ROW_BYTES + 3 * b_bytes : A_STAGE_BYTES + b_bytes;
     if (p.halo) {
         p.total_iters = 3 * (Cin / TBK);          // one stage per (kw, channel chunk): 12 MMAs
         p.iters_per_split = p.total_iters;
@@ -934,8 +963,8 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks) {
 
 }  // namespace
 
-int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
-    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks, int x_half) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks, x_half != 0);
     if (!p.ok || (Cout & 3) != 0 || p.BN > 192) return 0;
     if (p.csk) return (H * W) / p.csk_seg;               // cluster split-K: one slot per csk_seg rows
     if (p.splitk > 1) return splitk_reduce_slots(H * W);  // the split-K reduce emits one slot per 16 rows
@@ -944,8 +973,8 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks) {
     return (HW == 64 || HW == 32) ? 1 : 0;               // tiles of whole images aligned to the epilogue's row quarters
 }
 
-bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats) {
-    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats, int x_half) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks, x_half != 0);
     if (!p.ok) return false;
     *floats = (p.splitk > 1 && !p.csk) ? (size_t)p.splitk * p.M * Cout : 0;
     return true;
@@ -954,18 +983,23 @@ bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, si
 int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bias, const float* row_add,
                    int row_add_pitch, const float* residual, int res_pitch, float* y, int y_pitch, int B, int H,
                    int W, int Cin, int Cout, int ks, float* workspace, size_t workspace_floats, float* gn_partial,
-                   cudaStream_t st, int y_half, const float* x2, int x2_pitch, int Cin1) {
+                   cudaStream_t st, int y_half, const float* x2, int x2_pitch, int Cin1, int x_half) {
+    // x_half: x (and x2) and w hold fp16 elements (pitches in elements): tcgen05.mma.kind::f16, 64 channels per stage
+    const bool f16 = x_half != 0;
+    const int TBK = tbk(f16);
+    const int esz = f16 ? 2 : 4;                       // operand element size
+    const int pmask = f16 ? 7 : 3;                     // pixel pitch must keep rows 16-byte aligned (TMA global strides)
     // x2 != NULL: input channels [0, Cin1) are read from x, [Cin1, Cin) from x2 (torch.cat never materialised)
-    if (x2 != nullptr && (Cin1 <= 0 || Cin1 >= Cin || Cin1 % TBK != 0 || (x2_pitch & 3) != 0 || !aligned16(x2)))
+    if (x2 != nullptr && (Cin1 <= 0 || Cin1 >= Cin || Cin1 % TBK != 0 || (x2_pitch & pmask) != 0 || !aligned16(x2)))
         return AFLDM_E_NOKERNEL;
-    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks);
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks, f16);
     if (y_half && (!p.ok || p.splitk > 1 || residual != nullptr || gn_partial != nullptr || (Cout & 7) != 0 ||
                    (y_pitch & 7) != 0 || !aligned16(y) || (bias != nullptr && !aligned16(bias)) ||
                    (row_add != nullptr && ((row_add_pitch & 3) != 0 || !aligned16(row_add)))))
         return AFLDM_E_NOKERNEL;             // fp16 stores live in the vectorised un-split epilogue only
-    const int gn_slots = gn_partial != nullptr ? conv_tc_gn_slots(B, H, W, Cin, Cout, ks) : 0;
+    const int gn_slots = gn_partial != nullptr ? conv_tc_gn_slots(B, H, W, Cin, Cout, ks, x_half) : 0;
     if (gn_partial != nullptr && gn_slots == 0) return AFLDM_E_SHAPE;
-    if (!p.ok || (x_pitch & 3) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
+    if (!p.ok || (x_pitch & pmask) != 0 || !aligned16(x) || !aligned16(w)) return AFLDM_E_NOKERNEL;
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) return AFLDM_E_NOKERNEL;
     if (p.splitk > 1 && !p.csk && (workspace == nullptr || workspace_floats < (size_t)p.splitk * p.M * Cout))
@@ -974,10 +1008,11 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     CUtensorMap map_a, map_a2, map_b;
     auto encode_a = [&](CUtensorMap* m, const float* src, int pitch, int channels) {
         const cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * W, (cuuint64_t)pitch * 4 * W * H};
+        const cuuint64_t strides[3] = {(cuuint64_t)pitch * esz, (cuuint64_t)pitch * esz * W, (cuuint64_t)pitch * esz * W * H};
         const cuuint32_t box[4] = {(cuuint32_t)TBK, (cuuint32_t)p.BW, (cuuint32_t)(p.halo ? p.BH + 2 : p.BH), (cuuint32_t)p.BB};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(src), dims, strides, box, estr,
+        return enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(src),
+                   dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
@@ -990,10 +1025,11 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     {
         const cuuint64_t K = (cuuint64_t)ks * ks * Cin;
         const cuuint64_t dims[2] = {K, (cuuint64_t)Cout};
-        const cuuint64_t strides[1] = {K * 4};
+        const cuuint64_t strides[1] = {K * esz};
         const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)(p.two ? p.BN / 2 : p.BN)};
         const cuuint32_t estr[2] = {1, 1};
-        if (enc(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+        if (enc(&map_b, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w),
+                dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return AFLDM_E_NOKERNEL;
@@ -1002,8 +1038,10 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaSuccess;
-        const void* kerns[4] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<false, true>,
-                                (const void*)conv_tc_kernel<true, false>, (const void*)conv_tc_kernel<true, true>};
+        const void* kerns[8] = {(const void*)conv_tc_kernel<false, false, false>, (const void*)conv_tc_kernel<false, true, false>,
+                                (const void*)conv_tc_kernel<true, false, false>, (const void*)conv_tc_kernel<true, true, false>,
+                                (const void*)conv_tc_kernel<false, false, true>, (const void*)conv_tc_kernel<false, true, true>,
+                                (const void*)conv_tc_kernel<true, false, true>, (const void*)conv_tc_kernel<true, true, true>};
         for (const void* kp : kerns) {
             e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ONE_PER_SM + BARRIER_BYTES);
             if (e != cudaSuccess) return (int)e;
@@ -1045,7 +1083,8 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, map_a, map_a2, map_b, a);
+        if (f16) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, map_a, map_a2, map_b, a);
+        else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, false>, map_a, map_a2, map_b, a);
         return launched(1);
     }
     if (p.two) {
@@ -1061,12 +1100,19 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (p.halo) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, map_a, map_a2, map_b, a);
-        else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, map_a, map_a2, map_b, a);
+        if (p.halo) {
+            if (f16) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true>, map_a, map_a2, map_b, a);
+            else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, map_a, map_a2, map_b, a);
+        } else {
+            if (f16) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, true>, map_a, map_a2, map_b, a);
+            else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, false>, map_a, map_a2, map_b, a);
+        }
     } else if (p.halo) {
-        launch_k(conv_tc_kernel<false, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
+        if (f16) launch_k(conv_tc_kernel<false, true, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
+        else launch_k(conv_tc_kernel<false, true, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
     } else {
-        launch_k(conv_tc_kernel<false, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
+        if (f16) launch_k(conv_tc_kernel<false, false, true>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
+        else launch_k(conv_tc_kernel<false, false, false>, dim3(grid), dim3(TC_THREADS), p.smem_bytes, st, map_a, map_a2, map_b, a);
     }
     int launches = 1;
     if (p.splitk > 1) {

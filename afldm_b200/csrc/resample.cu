@@ -102,6 +102,7 @@ struct Affine {
     float eps;
     double inv_n;         // 1 / (HW * channels per group), from the host: no fp64 division in the prologue
     float2* gn_out;       // MODE_DOWN2 only: [B][1][C] (sum, sum of squares) of every output plane | NULL
+    int y_half;           // MODE_FACT: y holds IEEE binary16 (same indexing, in elements) - the operand of the next conv
     const float* x2;      // second input source: channels [xCa, C) are read from x2 (pixel pitch C - xCa), channels
     int xCa;              // [0, xCa) from x (pixel pitch xCa) - a skip-connection concat that is never materialised
 };
@@ -268,9 +269,16 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
 #pragma unroll
         for (int m = 0; m < M; ++m) a[m] = row[m * CG];
         down_line<N>(a, yl);
-        float* yp = y + ((size_t)(b * N + i) * N) * C + c0 + c;
+        const size_t yo = ((size_t)(b * N + i) * N) * C + c0 + c;
+        if (MODE == MODE_FACT && af.y_half) {
+            __half* yh = reinterpret_cast<__half*>(y) + yo;
 #pragma unroll
-        for (int j = 0; j < N; ++j) yp[(size_t)j * C] = yl[j];
+            for (int j = 0; j < N; ++j) yh[(size_t)j * C] = __float2half_rn(yl[j]);
+        } else {
+            float* yp = y + yo;
+#pragma unroll
+            for (int j = 0; j < N; ++j) yp[(size_t)j * C] = yl[j];
+        }
         if constexpr (MODE == MODE_DOWN2) {
             if (af.gn_out != nullptr) {
                 float ps = 0.f, pq = 0.f;
@@ -682,11 +690,20 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
         down_mma<N>(e, o, fd, acc);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            float* yp = y + ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
+            const size_t yo = ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
+            if (af.y_half) {
+                __half* yh = reinterpret_cast<__half*>(y) + yo;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) yp[(size_t)(8 * nt + 2 * t + q) * C] = acc[nt][2 * r + q];
+                    for (int q = 0; q < 2; ++q) yh[(size_t)(8 * nt + 2 * t + q) * C] = __float2half_rn(acc[nt][2 * r + q]);
+            } else {
+                float* yp = y + yo;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) yp[(size_t)(8 * nt + 2 * t + q) * C] = acc[nt][2 * r + q];
+            }
         }
     }
 }
@@ -735,6 +752,7 @@ int dispatch_n(const float* x, float* y, int B, int n, int C, const Affine& af, 
             if (n == 16) return launch_fact_mma<16, ACT>(x, y, B, C, af, st);
         }
     }
+    if (af.y_half && (MODE != MODE_FACT || n >= 32)) return AFLDM_E_NOKERNEL;   // fp16 stores: fact_mma + n <= 16 kernels
     switch (n) {
         case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, af, st);
         case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, af, st);
@@ -781,10 +799,10 @@ extern "C" int afldm_filtered_act_f32(const float* x, float* y, int B, int H, in
     return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, st);
 }
 
-extern "C" int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H, int W, int C, int act,
-                                         const float* partial_a, int slots_a, int Ca, const float* partial_b,
-                                         int slots_b, int Cb, int groups, float eps, const float* gamma,
-                                         const float* beta, afldm_stream_t stream) {
+static int filtered_act_gn_impl(const float* x, float* y, int y_half, int B, int H, int W, int C, int act,
+                                const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                const float* beta, afldm_stream_t stream) {
     if (bad_args(x, y, B, H, W, C, nullptr, nullptr) || partial_a == nullptr) return AFLDM_E_ARG;
     if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
     if (slots_a <= 0 || Ca <= 0 || Cb < 0 || groups <= 0 || (Cb > 0 && (partial_b == nullptr || slots_b <= 0)))
@@ -799,9 +817,27 @@ extern "C" int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H,
     af.slots_a = slots_a; af.Ca = Ca; af.slots_b = Cb > 0 ? slots_b : 0; af.Cb = Cb;
     af.groups = groups; af.HW = H * W; af.eps = eps;
     af.inv_n = 1.0 / ((double)(H * W) * (double)(C / groups));
+    af.y_half = y_half;
     cudaStream_t st = as_stream(stream);
     if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, y, B, H, C, af, st);
     return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, st);
+}
+
+extern "C" int afldm_filtered_act_gn_f32(const float* x, float* y, int B, int H, int W, int C, int act,
+                                         const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                         int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                         const float* beta, afldm_stream_t stream) {
+    return filtered_act_gn_impl(x, y, 0, B, H, W, C, act, partial_a, slots_a, Ca, partial_b, slots_b, Cb, groups, eps, gamma,
+                                beta, stream);
+}
+
+extern "C" int afldm_filtered_act_gn_f16out(const float* x, void* y, int B, int H, int W, int C, int act,
+                                            const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                            int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                            const float* beta, afldm_stream_t stream) {
+    if (static_cast<const void*>(x) == y) return AFLDM_E_ARG;          // element sizes differ: no in-place form
+    return filtered_act_gn_impl(x, static_cast<float*>(y), 1, B, H, W, C, act, partial_a, slots_a, Ca, partial_b, slots_b, Cb,
+                                groups, eps, gamma, beta, stream);
 }
 
 extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W, int C,
@@ -836,10 +872,10 @@ extern "C" int afldm_lpf_down2_gn_f32(const float* x, float* y, int B, int H, in
     return dispatch_n<MODE_DOWN2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, af, as_stream(stream));
 }
 
-extern "C" int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, float* y, int B, int H, int W, int Ca,
-                                             int Cb, int act, const float* partial_a, int slots_a,
-                                             const float* partial_b, int slots_b, int groups, float eps,
-                                             const float* gamma, const float* beta, afldm_stream_t stream) {
+static int filtered_act_gn_cat_impl(const float* xa, const float* xb, float* y, int y_half, int B, int H, int W, int Ca,
+                                    int Cb, int act, const float* partial_a, int slots_a,
+                                    const float* partial_b, int slots_b, int groups, float eps,
+                                    const float* gamma, const float* beta, afldm_stream_t stream) {
     const int C = Ca + Cb;
     if (xa == nullptr || xb == nullptr || y == nullptr || partial_a == nullptr || partial_b == nullptr) return AFLDM_E_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || Ca <= 0 || Cb <= 0 || slots_a <= 0 || slots_b <= 0 || groups <= 0) return AFLDM_E_ARG;
@@ -857,7 +893,24 @@ extern "C" int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, f
     af.groups = groups; af.HW = H * W; af.eps = eps;
     af.inv_n = 1.0 / ((double)(H * W) * (double)(C / groups));
     af.x2 = xb; af.xCa = Ca;
+    af.y_half = y_half;
     cudaStream_t st = as_stream(stream);
     if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(xa, y, B, H, C, af, st);
     return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(xa, y, B, H, C, af, st);
+}
+
+extern "C" int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, float* y, int B, int H, int W, int Ca,
+                                             int Cb, int act, const float* partial_a, int slots_a,
+                                             const float* partial_b, int slots_b, int groups, float eps,
+                                             const float* gamma, const float* beta, afldm_stream_t stream) {
+    return filtered_act_gn_cat_impl(xa, xb, y, 0, B, H, W, Ca, Cb, act, partial_a, slots_a, partial_b, slots_b, groups, eps,
+                                    gamma, beta, stream);
+}
+
+extern "C" int afldm_filtered_act_gn_cat_f16out(const float* xa, const float* xb, void* y, int B, int H, int W, int Ca,
+                                                int Cb, int act, const float* partial_a, int slots_a,
+                                                const float* partial_b, int slots_b, int groups, float eps,
+                                                const float* gamma, const float* beta, afldm_stream_t stream) {
+    return filtered_act_gn_cat_impl(xa, xb, static_cast<float*>(y), 1, B, H, W, Ca, Cb, act, partial_a, slots_a, partial_b,
+                                    slots_b, groups, eps, gamma, beta, stream);
 }

@@ -19,15 +19,23 @@ import torch.nn as nn
 
 from .. import ops
 from ..af_modules.af_blocks import WarpedNonlinearity, act_name
-from ..packing import conv_params, fused_linear_params
+from ..packing import conv_params, conv_params_f16, fused_linear_params
 
 
-def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module) -> torch.Tensor:
+def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module, out_half: bool = False) -> torch.Tensor:
     """act(GroupNorm(x)) on NHWC x: statistics pass + one fused apply kernel.
-    A ``WarpedNonlinearity`` (alias-free surgery) selects the filtered activation."""
+    A ``WarpedNonlinearity`` (alias-free surgery) selects the filtered activation.  ``out_half``: the only consumer
+    is a tensor-core convolution that accepts fp16 operands - the result MAY then be fp16 (check ``.dtype``)."""
     if isinstance(nonlinearity, WarpedNonlinearity):
-        return ops.filtered_act_groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=nonlinearity.act)
+        return ops.filtered_act_groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=nonlinearity.act,
+                                          out_half=out_half)
     return ops.groupnorm_act(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=act_name(nonlinearity))
+
+
+def conv_after_act(a: torch.Tensor, conv: nn.Module, **kw) -> torch.Tensor:
+    """``ops.conv2d`` of an activation that may have been stored as fp16 (``norm_act(out_half=True)``)."""
+    w, b, k = conv_params_f16(conv) if a.dtype == torch.float16 else conv_params(conv)
+    return ops.conv2d(a, w, b, k, **kw)
 
 
 class ResnetBlock2D(nn.Module):
@@ -56,14 +64,17 @@ class ResnetBlock2D(nn.Module):
         if temb_proj is None and temb is not None and self.time_emb_proj is not None:
             temb_proj = ops.linear_rows(temb.contiguous(), self.time_emb_proj.weight, self.time_emb_proj.bias,
                                         act_in="silu")
-        w1, b1, k1 = conv_params(self.conv1)
+        bsz, hh, ww = x.shape[0], x.shape[1], x.shape[2]
+        cin_total = self.conv1.in_channels
+        half1 = ops.conv_f16_supported(bsz, hh, ww, cin_total, self.out_channels)
+        half2 = ops.conv_f16_supported(bsz, hh, ww, self.out_channels, self.out_channels)
         act1, sc = None, None
         if skip is not None:
             xs = ops.nhwc(skip)
             if isinstance(self.nonlinearity, WarpedNonlinearity) and self.conv_shortcut is not None:
                 n1 = self.norm1
                 act1 = ops.filtered_act_groupnorm_cat(x, xs, n1.num_groups, n1.eps, n1.weight, n1.bias,
-                                                      act=self.nonlinearity.act)
+                                                      act=self.nonlinearity.act, out_half=half1)
                 if act1 is not None:
                     ws, bs, ks = conv_params(self.conv_shortcut)
                     sc = ops.conv2d_cat(x, xs, ws, bs, ks)
@@ -71,18 +82,17 @@ class ResnetBlock2D(nn.Module):
                 x = ops.concat_channels(x, xs)
                 act1 = None
         if act1 is None:
-            act1 = norm_act(x, self.norm1, self.nonlinearity)
-        h = ops.conv2d(act1, w1, b1, k1, row_add=temb_proj, gn_stats=True)
-        a = norm_act(h, self.norm2, self.nonlinearity)
-        w2, b2, k2 = conv_params(self.conv2)
+            act1 = norm_act(x, self.norm1, self.nonlinearity, out_half=half1)
+        h = conv_after_act(act1, self.conv1, row_add=temb_proj, gn_stats=True)
+        a = norm_act(h, self.norm2, self.nonlinearity, out_half=half2)
         if sc is not None:
-            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc, gn_stats=True)
+            out = conv_after_act(a, self.conv2, residual=sc, out=sc, gn_stats=True)
         elif self.conv_shortcut is not None:
             ws, bs, ks = conv_params(self.conv_shortcut)
             sc = ops.conv2d(x, ws, bs, ks)
-            out = ops.conv2d(a, w2, b2, k2, residual=sc, out=sc, gn_stats=True)
+            out = conv_after_act(a, self.conv2, residual=sc, out=sc, gn_stats=True)
         else:
-            out = ops.conv2d(a, w2, b2, k2, residual=x, gn_stats=True)
+            out = conv_after_act(a, self.conv2, residual=x, gn_stats=True)
         return ops.nchw_view(out)
 
 

@@ -169,8 +169,17 @@ def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: O
 FUSE_CONCAT = os.environ.get("AFLDM_FUSE_CONCAT", "1") == "1"
 
 
+def conv_f16_supported(b: int, h: int, w: int, cin: int, cout: int) -> bool:
+    """Shapes ``conv2d`` accepts with fp16 operands (mirrors the tcgen05 plan of csrc/conv_tc.cu with 64-channel
+    stages); the producer of the activation asks this BEFORE it decides to emit fp16."""
+    def pow2(v):
+        return v > 0 and (v & (v - 1)) == 0
+    return (F16_CONV and _default_conv_algo == "tf32" and cin % 64 == 0 and cout >= 16 and cout % 16 == 0
+            and pow2(h) and pow2(w) and (w <= 128 or w % 128 == 0) and b * h * w >= 1)
+
+
 def filtered_act_groupnorm_cat(a: torch.Tensor, b: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
-                               beta: Optional[torch.Tensor], act: str = "silu") -> Optional[torch.Tensor]:
+                               beta: Optional[torch.Tensor], act: str = "silu", out_half: bool = False) -> Optional[torch.Tensor]:
     """act-filtered GroupNorm(torch.cat([a, b], channels)) on NHWC a, b WITHOUT materialising the concat (norm1 of an
     up-block resnet).  Needs the GroupNorm partial sums of both producers; returns None when this form does not
     apply (missing sums, planes > 32, channel groups straddling the sources) - the caller then concatenates."""
@@ -183,15 +192,22 @@ def filtered_act_groupnorm_cat(a: torch.Tensor, b: torch.Tensor, groups: int, ep
     cb = b.shape[-1]
     if b.shape[:-1] != a.shape[:-1] or h != w or h > 32 or ga[2] != ca or gb[2] != cb:
         return None
-    out = torch.empty((bsz, h, w, ca + cb), dtype=torch.float32, device=a.device)
     L = _lib.lib()
+    out = None
 
     def call():
-        return L.afldm_filtered_act_gn_cat_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), bsz, h, w, ca, cb, ACT[act],
-                                               ga[0].data_ptr(), ga[1], gb[0].data_ptr(), gb[1], groups, float(eps),
-                                               _ptr(gamma), _ptr(beta), _stream())
+        fn = L.afldm_filtered_act_gn_cat_f16out if out.dtype == torch.float16 else L.afldm_filtered_act_gn_cat_f32
+        return fn(a.data_ptr(), b.data_ptr(), out.data_ptr(), bsz, h, w, ca, cb, ACT[act],
+                  ga[0].data_ptr(), ga[1], gb[0].data_ptr(), gb[1], groups, float(eps),
+                  _ptr(gamma), _ptr(beta), _stream())
 
-    code = call()
+    code = -3
+    if out_half:          # fp16 result for a tensor-core consumer; -3 = this plane size only has the fp32 kernel
+        out = torch.empty((bsz, h, w, ca + cb), dtype=torch.float16, device=a.device)
+        code = call()
+    if code == -3:
+        out = torch.empty((bsz, h, w, ca + cb), dtype=torch.float32, device=a.device)
+        code = call()
     if code == -3:
         return None
     _lib.check(code, "filtered_act_gn_cat")
@@ -240,7 +256,7 @@ def conv2d_cat(a: torch.Tensor, b: torch.Tensor, w_packed: torch.Tensor, bias: O
 
 
 def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
-                           beta: Optional[torch.Tensor], act: str = "silu") -> torch.Tensor:
+                           beta: Optional[torch.Tensor], act: str = "silu", out_half: bool = False) -> torch.Tensor:
     """act-filtered GroupNorm(x) on NHWC x: statistics pass (or finalize of the producer's partial sums) +
     filtered activation.  ``FUSE_GN_PROLOGUE`` selects the one-launch variant that finalises the statistics
     in the resampling kernel's prologue (afldm_filtered_act_gn_f32): one warp per touched group adds the producer's
@@ -252,8 +268,25 @@ def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Opti
     if FUSE_GN_PROLOGUE and (one is not None or two is not None) and h <= 32 and h == w:
         (pa, sa, ca), (pb, sb, cb) = (one, (None, 0, 0)) if one is not None else two
         if ca + cb == c:
-            out = torch.empty_like(x)
             L = _lib.lib()
+            if out_half:
+                # ``out_half``: fp16 result (consumed by a tensor-core convolution only); falls through to fp32 where
+                # the library has no fp16 store for this plane size (-3)
+                outh = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+
+                def call_h():
+                    return L.afldm_filtered_act_gn_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, ACT[act],
+                                                          pa.data_ptr(), sa, ca, _ptr(pb), sb, cb, groups, float(eps),
+                                                          _ptr(gamma), _ptr(beta), _stream())
+
+                code = call_h()
+                if code != -3:
+                    _lib.check(code, "filtered_act_gn_f16out")
+                    if _recorder is not None:
+                        _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), fused_gn=1, f16out=1),
+                                          call_h, (x, outh, pa, pb, gamma, beta)))
+                    return outh
+            out = torch.empty_like(x)
             _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), fused_gn=1),
                  lambda: L.afldm_filtered_act_gn_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act], pa.data_ptr(),
                                                      sa, ca, _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma),
@@ -386,8 +419,11 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     L = _lib.lib()
     b, h, w_, cin = x.shape
     cout = w_packed.shape[0]
-    if x.stride(-1) != 1 or not x.is_cuda or x.dtype != torch.float32:
-        raise _lib.AfldmError("conv2d: fp32 CUDA NHWC tensor expected")
+    if x.stride(-1) != 1 or not x.is_cuda or x.dtype not in (torch.float32, torch.float16):
+        raise _lib.AfldmError("conv2d: fp32 (or fp16) CUDA NHWC tensor expected")
+    f16in = x.dtype == torch.float16
+    if f16in != (w_packed.dtype == torch.float16):
+        raise _lib.AfldmError("conv2d: an fp16 activation needs the fp16-packed weight (packing.conv_params_f16) and vice versa")
     x_pitch = _pitch(x)
     if out is None:
         out = torch.empty((b, h, w_, cout), dtype=torch.float32, device=x.device)
@@ -405,6 +441,21 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     for stale in ("_afldm_gn", "_afldm_gn2"):
         if hasattr(out, stale):
             delattr(out, stale)
+
+    if f16in:
+        # fp16 operands (tcgen05.mma.kind::f16): tensor-core path only, no SIMT form
+        need = L.afldm_conv2d_workspace_floats(b, h, w_, cin, cout, ksize, 2)
+        ws = scratch(x.device, need) if need else None
+        slots = L.afldm_conv2d_gn_slots(b, h, w_, cin, cout, ksize, 2) if gn_stats else 0
+        gn = torch.empty((b, slots, cout, 2), dtype=torch.float32, device=x.device) if slots else None
+        meta["f16in"] = 1
+        _run("conv2d_f16", meta,
+             lambda: L.afldm_conv2d_f16in_f32(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), _ptr(row_add), ra_pitch,
+                                              _ptr(residual), res_pitch, out.data_ptr(), y_pitch, b, h, w_, cin, cout, ksize,
+                                              _ptr(ws), need, _ptr(gn), _stream()), keep + (ws, gn))
+        if gn is not None:
+            out._afldm_gn = (gn, slots, cout)
+        return out
 
     def call(a: int, ws, need: int, gn=None):
         return L.afldm_conv2d_f32(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), _ptr(row_add), ra_pitch,
@@ -431,6 +482,9 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
 
 
 F16_ATTENTION = os.environ.get("AFLDM_ATTN_F16", "1") == "1"
+# TF32 class: the filtered activation in front of a resnet convolution stores fp16 (the 11 significant bits the tensor
+# core would keep of it anyway) and the convolution runs tcgen05.mma.kind::f16 on fp16-packed weights
+F16_CONV = os.environ.get("AFLDM_CONV_F16", "1") == "1"
 
 
 def conv2d_f16out(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], ksize: int) -> Optional[torch.Tensor]:

@@ -36,6 +36,18 @@ def conv_params(m: nn.Module) -> Tuple[torch.Tensor, Optional[torch.Tensor], int
     return cache[1]
 
 
+def conv_params_f16(m: nn.Module) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
+    """``conv_params`` with the packed weight rounded to fp16 (the B operand of ``ops.conv2d`` on an fp16 activation:
+    tcgen05.mma.kind::f16 keeps the same 11 significant bits TF32 does, in half the bytes)."""
+    key = _key((m.weight, m.bias))
+    cache = getattr(m, "_afldm_pack_f16", None)
+    if cache is None or cache[0] != key:
+        w, bias, k = conv_params(m)
+        cache = (key, (w.to(torch.float16).contiguous(), bias, k))
+        object.__setattr__(m, "_afldm_pack_f16", cache)
+    return cache[1]
+
+
 def fused_linear_params(owner: nn.Module, tag: str, layers: Sequence[nn.Module]):
     """Row-concatenated weight / bias of several nn.Linear (or 1x1 conv) layers sharing an input:
     q|k|v of an attention block, or every resnet's time_emb_proj of a UNet."""

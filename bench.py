@@ -400,7 +400,9 @@ def main():
                         "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(name), "launches_per_step": a["launches"],
                         "avg_launch_ms": a["ms"] / a["launches"],
                         "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step's launch mix); "
-                                       "operands are TF32, whose tensor peak is half the bf16 peak",
+                                       + ("operands are fp16 (tcgen05.mma.kind::f16), the same tensor rate as bf16"
+                                          if name == "conv2d_f16" else
+                                          "operands are TF32, whose tensor peak is half the bf16 peak"),
                         "algorithmic_flops_per_step": a["flops"], "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_traffic.json)"}
         else:
             ach = a["bytes"] / (a["ms"] / 1e3) / 1e9
@@ -430,9 +432,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("f32 storage; tensor-core products on 11-bit-significand operands (conv: tf32; attention q/k/v: fp16 "
-                      "containers of the same significand width; filtered activation: 3-term fp16 split = fp32 accuracy), "
-                      "fp32 accumulate") if args.conv_algo == "tf32" else "f32",
+            "dtype": ("f32 residual stream / norms / softmax / accumulation; tensor-core products on 11-bit-significand "
+                      "operands (resnet 3x3 convs: fp16 operands written by the filtered activation, kind::f16; other "
+                      "convs / projections: tf32; attention q/k/v: fp16; filtered activation: 3-term fp16 split = fp32 "
+                      "accuracy)") if args.conv_algo == "tf32" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "conv_algo": args.conv_algo, "cuda_graph": True,

@@ -42,7 +42,7 @@ enum {
 };
 
 enum { AFLDM_ACT_IDENTITY = 0, AFLDM_ACT_SILU = 1 };
-enum { AFLDM_CONV_SIMT_F32 = 0, AFLDM_CONV_TCGEN05_TF32 = 1 };
+enum { AFLDM_CONV_SIMT_F32 = 0, AFLDM_CONV_TCGEN05_TF32 = 1, AFLDM_CONV_TCGEN05_F16 = 2 /* plan queries of afldm_conv2d_f16in_f32 */ };
 enum { AFLDM_ATTN_SIMT_F32 = 0, AFLDM_ATTN_MMA_TF32 = 1 };
 
 /* Library / build identification. abi = 1. */
@@ -88,6 +88,20 @@ AFLDM_API int afldm_filtered_act_gn_cat_f32(const float* xa, const float* xb, fl
                                   int Cb, int act, const float* partial_a, int slots_a,
                                   const float* partial_b, int slots_b, int groups, float eps,
                                   const float* gamma, const float* beta, afldm_stream_t stream);
+
+/* afldm_filtered_act_gn_f32 / afldm_filtered_act_gn_cat_f32 with an fp16 result (y: IEEE binary16 NHWC, C halves per
+ * pixel): the activation is consumed only by the resnet's next convolution (diffusers ResnetBlock2D conv1 / conv2,
+ * SURVEY.md 8a-R), whose tensor-core products round their operands to 11 significant bits anyway - storing those 11
+ * bits (fp16, round to nearest) halves the bytes the convolution stages (afldm_conv2d_f16in_f32).  |y| < 65504.
+ * AFLDM_E_NOKERNEL where only the exact-FMA n = 32 kernel applies (AFLDM_FACT_MMA=0) and for planes above 32 x 32. */
+AFLDM_API int afldm_filtered_act_gn_f16out(const float* x, void* y, int B, int H, int W, int C, int act,
+                                           const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                           int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                           const float* beta, afldm_stream_t stream);
+AFLDM_API int afldm_filtered_act_gn_cat_f16out(const float* xa, const float* xb, void* y, int B, int H, int W, int Ca,
+                                               int Cb, int act, const float* partial_a, int slots_a,
+                                               const float* partial_b, int slots_b, int groups, float eps,
+                                               const float* gamma, const float* beta, afldm_stream_t stream);
 
 /* UpsampleRFFT(up=2).forward (afldm/af_libs/ideal_lpf.py:148-158), optional affine on load:
  * x NHWC [B,H,W,C] -> y NHWC [B,2H,2W,C]. */
@@ -181,6 +195,18 @@ AFLDM_API int afldm_conv2d_cat_f32(const float* xa, int xa_pitch, int Ca, const 
  * and the fp32-input attention). */
 AFLDM_API int afldm_conv2d_f16out(const float* x, int x_pitch, const float* w, const float* bias, void* y, int y_pitch,
                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
+
+/* afldm_conv2d_f32 (tensor-core path) with fp16 OPERANDS: x is IEEE binary16 NHWC (row pitch x_pitch halves, a multiple
+ * of 8), w is the packed weight [Cout][k*k][Cin] rounded to binary16; tcgen05.mma.kind::f16, fp32 accumulation in TMEM,
+ * fp32 epilogue and output exactly as afldm_conv2d_f32.  Same numeric class as AFLDM_CONV_TCGEN05_TF32 (products of
+ * 11-bit significands, fp32 sums) at half the operand bytes and twice the K per instruction.  Cin % 64 == 0.
+ * Plan queries: afldm_conv2d_workspace_floats / afldm_conv2d_gn_slots with algo = AFLDM_CONV_TCGEN05_F16.
+ * AFLDM_E_NOKERNEL outside the family (callers keep fp32 activations and use afldm_conv2d_f32). */
+AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, const float* bias,
+                                     const float* row_add, int row_add_pitch, const float* residual, int res_pitch,
+                                     float* y, int y_pitch, int B, int H, int W, int Cin, int Cout, int ksize,
+                                     float* workspace, size_t workspace_floats, float* gn_partial,
+                                     afldm_stream_t stream);
 
 /* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
  * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */
