@@ -32,12 +32,14 @@ SIGNATURES = {
     "afldm_filtered_act_gn_f16out": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
     "afldm_filtered_act_gn_cat_f16out": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _f, _p, _p, _p]),
     "afldm_up2_ideal_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "afldm_up2_ideal_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "afldm_lpf_down2_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
     "afldm_lpf_down2_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "afldm_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),
     "afldm_groupnorm_affine_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "afldm_affine_act_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "afldm_affine_act_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
+    "afldm_affine_act_gn_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
     "afldm_conv2d_workspace_floats": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "afldm_conv2d_gn_slots": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "afldm_conv2d_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
@@ -47,6 +49,8 @@ SIGNATURES = {
     "afldm_linear_rows_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "afldm_attention_f32": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_attention_f16": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "afldm_attention_f16_f16out": (_i, [_p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "afldm_conv2d_f16in_f16out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_conv2d_f16out": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_softmax_rows_f32": (_i, [_p, _ll, _i, _i, _f, _p]),
     "afldm_timestep_embedding_f32": (_i, [_p, _p, _i, _i, _p]),

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..packing import conv_params
+from ..packing import conv_params, conv_params_f16
 
 
 def act_name(nonlinearity: nn.Module) -> str:
@@ -57,10 +57,14 @@ class AliasFreeUpsample2D(nn.Module):
 
     def forward(self, hidden_states: torch.Tensor, output_size=None, *args, **kwargs) -> torch.Tensor:
         assert hidden_states.shape[1] == self.channels
-        h = ops.up2_ideal(ops.nhwc(hidden_states))
-        if self.use_conv:
-            w, b, k = conv_params(self.conv)
-            h = ops.conv2d(h, w, b, k, gn_stats=True)       # feeds the next block's GroupNorm (via the skip concat)
+        x = ops.nhwc(hidden_states)
+        if not self.use_conv:
+            return ops.nchw_view(ops.up2_ideal(x))
+        # TF32 class: the up-sampled tensor is read by the convolution only - stored as fp16 (kind::f16 operands)
+        half = ops.conv_f16_supported(x.shape[0], 2 * x.shape[1], 2 * x.shape[2], self.channels, self.out_channels)
+        h = ops.up2_ideal(x, out_half=half)
+        w, b, k = conv_params_f16(self.conv) if h.dtype == torch.float16 else conv_params(self.conv)
+        h = ops.conv2d(h, w, b, k, gn_stats=True)           # feeds the next block's GroupNorm (via the skip concat)
         return ops.nchw_view(h)
 
 

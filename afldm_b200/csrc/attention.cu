@@ -434,7 +434,7 @@ template <int D, int MT>
 __global__ void __launch_bounds__(128, MT == 2 ? 4 : 5)
 attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __restrict__ k,
                      const __half* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
-                     int Bkv_rep, int Nq, int Nk, float scale_log2e) {
+                     int Bkv_rep, int Nq, int Nk, float scale_log2e, int o_half) {
     pdl_trigger();
     constexpr int KT = 64;                       // keys per tile
     constexpr int DP = (D + 15) / 16 * 16;       // head dim padded to the MMA k (zero columns)
@@ -633,6 +633,23 @@ attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __
         l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
         const int r0 = wrow + mt * 16 + g, r1 = r0 + 8;
+        if (o_half) {
+            // fp16 result (o_pitch in halves): the A operand of the to_out projection (afldm_conv2d_f16in_f32)
+            __half* oh = reinterpret_cast<__half*>(o);
+            if (r0 < Nq) {
+                __half* op = oh + ((size_t)b * Nq + r0) * o_pitch + head * D + 2 * t;
+#pragma unroll
+                for (int dn = 0; dn < DN; ++dn)
+                    *reinterpret_cast<__half2*>(op + 8 * dn) = __floats2half2_rn(oacc[mt][dn][0] * i0, oacc[mt][dn][1] * i0);
+            }
+            if (r1 < Nq) {
+                __half* op = oh + ((size_t)b * Nq + r1) * o_pitch + head * D + 2 * t;
+#pragma unroll
+                for (int dn = 0; dn < DN; ++dn)
+                    *reinterpret_cast<__half2*>(op + 8 * dn) = __floats2half2_rn(oacc[mt][dn][2] * i1, oacc[mt][dn][3] * i1);
+            }
+            continue;
+        }
         if (r0 < Nq) {
             float* op = o + ((size_t)b * Nq + r0) * o_pitch + head * D + 2 * t;
 #pragma unroll
@@ -650,7 +667,7 @@ attention_f16_kernel(const __half* __restrict__ q, int q_pitch, const __half* __
 
 template <int D, int MT>
 int launch_f16_mt(const __half* q, int q_pitch, const __half* k, const __half* v, int kv_pitch, float* o, int o_pitch,
-                  int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+                  int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st, int o_half) {
     const float scale_log2e = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
     constexpr int DP = (D + 15) / 16 * 16;
     constexpr int smem = 4 * 64 * (DP + 8) * 2;
@@ -661,17 +678,17 @@ int launch_f16_mt(const __half* q, int q_pitch, const __half* k, const __half* v
     }
     configured = true;
     launch_k(attention_f16_kernel<D, MT>, dim3(ceil_div(Nq, 64 * MT), heads, B), dim3(128), smem, st,
-        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, scale_log2e);
+        q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, scale_log2e, o_half);
     return launched();
 }
 
 template <int D>
 int launch_f16(const __half* q, int q_pitch, const __half* k, const __half* v, int kv_pitch, float* o, int o_pitch,
-               int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st) {
+               int B, int Bkv, int Nq, int Nk, int heads, cudaStream_t st, int o_half) {
     static const int force_mt = getenv("AFLDM_ATTN_MT") ? atoi(getenv("AFLDM_ATTN_MT")) : 0;
     if (force_mt != 1 && D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
-        return launch_f16_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
-    return launch_f16_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+        return launch_f16_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st, o_half);
+    return launch_f16_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st, o_half);
 }
 
 template <int D>
@@ -740,9 +757,9 @@ extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, 
 #undef AFLDM_ATT_CASE
 }
 
-extern "C" int afldm_attention_f16(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch, float* o,
-                                   int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
-                                   afldm_stream_t stream) {
+static int attention_f16_impl(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch, float* o,
+                              int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                              afldm_stream_t stream, int o_half) {
     if (q == nullptr || k == nullptr || v == nullptr || o == nullptr) return AFLDM_E_ARG;
     if (B <= 0 || Bkv <= 0 || Nq <= 0 || Nk <= 0 || heads <= 0 || d <= 0) return AFLDM_E_ARG;
     if (B % Bkv != 0) return AFLDM_E_SHAPE;
@@ -754,7 +771,7 @@ extern "C" int afldm_attention_f16(const void* q, int q_pitch, const void* k, co
     const __half* kh = static_cast<const __half*>(k);
     const __half* vh = static_cast<const __half*>(v);
 #define AFLDM_ATT_F16(D) \
-    case D: return launch_f16<D>(qh, q_pitch, kh, vh, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    case D: return launch_f16<D>(qh, q_pitch, kh, vh, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st, o_half);
     switch (d) {
         AFLDM_ATT_F16(8)
         AFLDM_ATT_F16(16)
@@ -766,4 +783,17 @@ extern "C" int afldm_attention_f16(const void* q, int q_pitch, const void* k, co
         default: return AFLDM_E_NOKERNEL;
     }
 #undef AFLDM_ATT_F16
+}
+
+extern "C" int afldm_attention_f16(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch, float* o,
+                                   int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                                   afldm_stream_t stream) {
+    return attention_f16_impl(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, d, stream, 0);
+}
+
+extern "C" int afldm_attention_f16_f16out(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch, void* o,
+                                          int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                                          afldm_stream_t stream) {
+    if ((reinterpret_cast<uintptr_t>(o) & 3u) != 0) return AFLDM_E_ARG;
+    return attention_f16_impl(q, q_pitch, k, v, kv_pitch, static_cast<float*>(o), o_pitch, B, Bkv, Nq, Nk, heads, d, stream, 1);
 }

@@ -78,6 +78,16 @@ extern "C" int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w,
                           Cout, ksize, workspace, workspace_floats, gn_partial, as_stream(stream), 0, nullptr, 0, 0, 1);
 }
 
+extern "C" int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
+                                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream) {
+    const float* xf = static_cast<const float*>(x);
+    const float* wf = static_cast<const float*>(w);
+    if (conv_bad_args(xf, x_pitch, wf, static_cast<const float*>(y), y_pitch, nullptr, 0, nullptr, 0, B, H, W, Cin, Cout, ksize))
+        return AFLDM_E_ARG;
+    return conv_tc_launch(xf, x_pitch, wf, bias, nullptr, 0, nullptr, 0, static_cast<float*>(y), y_pitch, B, H, W, Cin, Cout,
+                          ksize, nullptr, 0, nullptr, as_stream(stream), 1, nullptr, 0, 0, 1);
+}
+
 extern "C" int afldm_conv2d_cat_f32(const float* xa, int xa_pitch, int Ca, const float* xb, int xb_pitch, int Cb,
                                     const float* w, const float* bias, const float* row_add, int row_add_pitch,
                                     const float* residual, int res_pitch, float* y, int y_pitch, int B, int H, int W,

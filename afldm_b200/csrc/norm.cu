@@ -11,6 +11,8 @@
 //                scale / shift.  One launch, no scratch, fixed reduction order (deterministic).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace afldm {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(1024)
 affine_act_gn_kernel(const float4* __restrict__ x, float4* __restrict__ y, int HW, int C,
                      const float2* __restrict__ pa, int slots_a, int Ca, const float2* __restrict__ pb, int slots_b,
                      int Cb, const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
-                     double inv_n) {
+                     double inv_n, int y_half) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float s_aff[];                  // [C] scale | [C] shift | [groups] mean | [groups] rstd
@@ -228,7 +230,16 @@ affine_act_gn_kernel(const float4* __restrict__ x, float4* __restrict__ y, int H
         v.y = apply_act<ACT>(fmaf(v.y, sc.y, sh.y));
         v.z = apply_act<ACT>(fmaf(v.z, sc.z, sh.z));
         v.w = apply_act<ACT>(fmaf(v.w, sc.w, sh.w));
-        yb[i] = v;
+        if (y_half) {
+            // fp16 result (the A operand of the q | k | v projection): 8-byte stores, same element indexing
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(y)[(size_t)b * per_image4 + i] = pk;
+        } else {
+            yb[i] = v;
+        }
     }
 }
 
@@ -289,10 +300,10 @@ extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int
     return launched();
 }
 
-extern "C" int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, int C, int act,
-                                       const float* partial_a, int slots_a, int Ca, const float* partial_b,
-                                       int slots_b, int Cb, int groups, float eps, const float* gamma,
-                                       const float* beta, afldm_stream_t stream) {
+static int affine_act_gn_impl(const float* x, float* y, int y_half, int B, int HW, int C, int act,
+                              const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                              int slots_b, int Cb, int groups, float eps, const float* gamma,
+                              const float* beta, afldm_stream_t stream) {
     if (x == nullptr || y == nullptr || partial_a == nullptr || B <= 0 || HW <= 0 || C <= 0) return AFLDM_E_ARG;
     if (slots_a <= 0 || Ca <= 0 || Cb < 0 || groups <= 0 || (Cb > 0 && (partial_b == nullptr || slots_b <= 0)))
         return AFLDM_E_ARG;
@@ -312,11 +323,28 @@ extern "C" int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, 
     auto y4 = reinterpret_cast<float4*>(y);
     if (act == AFLDM_ACT_SILU)
         launch_k(affine_act_gn_kernel<AFLDM_ACT_SILU>, dim3(chunks, B), dim3(1024), smem, st, x4, y4, HW, C, pa, slots_a, Ca,
-                 pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n);
+                 pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n, y_half);
     else if (act == AFLDM_ACT_IDENTITY)
         launch_k(affine_act_gn_kernel<AFLDM_ACT_IDENTITY>, dim3(chunks, B), dim3(1024), smem, st, x4, y4, HW, C, pa, slots_a,
-                 Ca, pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n);
+                 Ca, pb, Cb > 0 ? slots_b : 0, Cb, gamma, beta, groups, eps, inv_n, y_half);
     else
         return AFLDM_E_ARG;
     return launched();
+}
+
+extern "C" int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, int C, int act,
+                                       const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                       int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                       const float* beta, afldm_stream_t stream) {
+    return affine_act_gn_impl(x, y, 0, B, HW, C, act, partial_a, slots_a, Ca, partial_b, slots_b, Cb, groups, eps, gamma, beta,
+                              stream);
+}
+
+extern "C" int afldm_affine_act_gn_f16out(const float* x, void* y, int B, int HW, int C, int act,
+                                          const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                          int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                          const float* beta, afldm_stream_t stream) {
+    if (static_cast<const void*>(x) == y) return AFLDM_E_ARG;
+    return affine_act_gn_impl(x, static_cast<float*>(y), 1, B, HW, C, act, partial_a, slots_a, Ca, partial_b, slots_b, Cb,
+                              groups, eps, gamma, beta, stream);
 }

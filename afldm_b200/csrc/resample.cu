@@ -102,7 +102,7 @@ struct Affine {
     float eps;
     double inv_n;         // 1 / (HW * channels per group), from the host: no fp64 division in the prologue
     float2* gn_out;       // MODE_DOWN2 only: [B][1][C] (sum, sum of squares) of every output plane | NULL
-    int y_half;           // MODE_FACT: y holds IEEE binary16 (same indexing, in elements) - the operand of the next conv
+    int y_half;           // MODE_FACT / MODE_UP2: y holds IEEE binary16 (same indexing, in elements) - the operand of the next conv
     const float* x2;      // second input source: channels [xCa, C) are read from x2 (pixel pitch C - xCa), channels
     int xCa;              // [0, xCa) from x (pixel pitch xCa) - a skip-connection concat that is never materialised
 };
@@ -234,7 +234,17 @@ resample_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
             for (int i = 0; i < N; ++i) col[i] = tile[i * PITCH + jj * CG + c];
             up_odd<N>(col, od);
             if constexpr (MODE == MODE_UP2) {
-                float* yp = y + ((size_t)(b * M) * M + jj) * C + c0 + c;
+                const size_t yo = ((size_t)(b * M) * M + jj) * C + c0 + c;
+                if (af.y_half) {
+                    __half* yh = reinterpret_cast<__half*>(y) + yo;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        yh[(size_t)(2 * i) * M * C] = __float2half_rn(apply_act<ACT>(col[i]));
+                        yh[(size_t)(2 * i + 1) * M * C] = __float2half_rn(apply_act<ACT>(od[i]));
+                    }
+                    continue;
+                }
+                float* yp = y + yo;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     yp[(size_t)(2 * i) * M * C] = apply_act<ACT>(col[i]);
@@ -752,7 +762,7 @@ int dispatch_n(const float* x, float* y, int B, int n, int C, const Affine& af, 
             if (n == 16) return launch_fact_mma<16, ACT>(x, y, B, C, af, st);
         }
     }
-    if (af.y_half && (MODE != MODE_FACT || n >= 32)) return AFLDM_E_NOKERNEL;   // fp16 stores: fact_mma + n <= 16 kernels
+    if (af.y_half && (MODE == MODE_DOWN2 || n >= 32)) return AFLDM_E_NOKERNEL;   // fp16 stores: fact_mma + n <= 16 kernels
     switch (n) {
         case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, af, st);
         case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, af, st);
@@ -849,6 +859,16 @@ extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W
     if (H > 32)
         return resample_large(MODE_UP2, AFLDM_ACT_IDENTITY, x, y, B, H, C, scale, shift, workspace, workspace_floats, st);
     return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, plain_affine(scale, shift), st);
+}
+
+extern "C" int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, afldm_stream_t stream) {
+    if (bad_args(x, static_cast<const float*>(y), B, H, W, C, nullptr, nullptr) || static_cast<const void*>(x) == y)
+        return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;
+    if (H > 16) return AFLDM_E_NOKERNEL;      // fp16 stores live in the register-resident kernels (n <= 16)
+    Affine af = plain_affine(nullptr, nullptr);
+    af.y_half = 1;
+    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, static_cast<float*>(y), B, H, C, af, as_stream(stream));
 }
 
 extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,

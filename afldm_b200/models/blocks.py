@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..af_modules.af_blocks import WarpedNonlinearity, act_name
-from ..packing import conv_params, conv_params_f16, fused_linear_params
+from ..packing import conv_params, conv_params_f16, fused_linear_params, fused_linear_params_f16
 
 
 def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module, out_half: bool = False) -> torch.Tensor:
@@ -110,19 +110,30 @@ class AttnProcessor2_0:
             raise NotImplementedError("attention_mask is not used on the AF-LDM path")
         x = ops.nhwc(hidden_states)
         b, h, w, c = x.shape
-        xn = x
-        if attn.group_norm is not None:
-            gn = attn.group_norm
-            xn = ops.groupnorm_act(x, gn.num_groups, gn.eps, gn.weight, gn.bias, act="identity")
         d = c // attn.heads
         # TF32 class: the projections may hand q | k | v over as fp16 (same 11-bit significands as TF32 operands)
         # to the ldmatrix / mma.m16n8k16 attention kernel
         f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and d <= 64 and d % 8 == 0
+        # ... and then the normalised input and the attention output, each consumed by ONE projection, are stored as
+        # fp16 too (kind::f16 projections: half the operand bytes)
+        half = (f16 and encoder_hidden_states is None and attn.group_norm is not None
+                and ops.conv_f16_supported(b, h, w, c, 3 * c))
+        xn = x
+        if attn.group_norm is not None:
+            gn = attn.group_norm
+            xn = ops.groupnorm_act(x, gn.num_groups, gn.eps, gn.weight, gn.bias, act="identity", out_half=half)
         if encoder_hidden_states is None:
-            wqkv, bqkv = fused_linear_params(attn, "qkv", (attn.to_q, attn.to_k, attn.to_v))
-            qkv = ops.conv2d_f16out(xn, wqkv, bqkv, 1) if f16 else None
-            if qkv is None:
-                qkv = ops.conv2d(xn, wqkv, bqkv, 1)
+            qkv = None
+            if xn.dtype == torch.float16:
+                wqkv, bqkv = fused_linear_params_f16(attn, "qkv", (attn.to_q, attn.to_k, attn.to_v))
+                qkv = ops.conv2d_f16out(xn, wqkv, bqkv, 1)
+                if qkv is None:         # split-K shape (small batch): fp32 q | k | v and the TF32-operand attention
+                    qkv = ops.conv2d(xn, wqkv, bqkv, 1)
+            else:
+                wqkv, bqkv = fused_linear_params(attn, "qkv", (attn.to_q, attn.to_k, attn.to_v))
+                qkv = ops.conv2d_f16out(xn, wqkv, bqkv, 1) if f16 else None
+                if qkv is None:
+                    qkv = ops.conv2d(xn, wqkv, bqkv, 1)
             qkv = qkv.view(b, h * w, 3 * c)
             q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
         else:
@@ -136,14 +147,13 @@ class AttnProcessor2_0:
             kv = ops.conv2d(src.view(src.shape[0], src.shape[1], 1, c), wkv, bkv, 1).view(src.shape[0], src.shape[1], 2 * c)
             k, v = kv[:, :, :c], kv[:, :, c:]
         if q.dtype == torch.float16 and k.dtype == torch.float16:
-            o = ops.attention_f16(q, k, v, attn.heads)
+            o = ops.attention_f16(q, k, v, attn.heads, out_half=xn.dtype == torch.float16)
         elif d <= 64 and d % 8 == 0:
             o = ops.attention(q, k, v, attn.heads)
         else:
             o = ops.attention_gemm(q, k, v, attn.heads)
-        wo, bo, _ = conv_params(attn.to_out[0])
-        out = ops.conv2d(o.view(b, h, w, c), wo, bo, 1, residual=x if attn.residual_connection else None,
-                         gn_stats=True)
+        out = conv_after_act(o.view(b, h, w, c), attn.to_out[0], residual=x if attn.residual_connection else None,
+                             gn_stats=True)
         if attn.rescale_output_factor != 1.0:
             raise NotImplementedError("rescale_output_factor != 1")
         return ops.nchw_view(out)

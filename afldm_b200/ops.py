@@ -297,10 +297,24 @@ def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Opti
 
 
 def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
-              shift: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """UpsampleRFFT(2) (ideal_lpf.py:148-158) on NHWC x."""
+              shift: Optional[torch.Tensor] = None, out_half: bool = False) -> torch.Tensor:
+    """UpsampleRFFT(2) (ideal_lpf.py:148-158) on NHWC x.  ``out_half``: the result MAY be fp16 (planes up to 16 x 16;
+    for a tensor-core convolution as the only consumer)."""
     _chk(x, "x")
     b, h, w, c = x.shape
+    if out_half and scale is None and h == w and h <= 16:
+        outh = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
+        Lh = _lib.lib()
+
+        def call_h():
+            return Lh.afldm_up2_ideal_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, _stream())
+
+        code = call_h()
+        if code != -3:
+            _lib.check(code, "up2_ideal_f16out")
+            if _recorder is not None:
+                _recorder.append(("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h, (x, outh)))
+            return outh
     out = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     need = L.afldm_resample_workspace_floats(1, b, h, w, c)
@@ -379,7 +393,7 @@ def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[t
 
 
 def groupnorm_act(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],
-                  beta: Optional[torch.Tensor], act: str = "identity") -> torch.Tensor:
+                  beta: Optional[torch.Tensor], act: str = "identity", out_half: bool = False) -> torch.Tensor:
     """act(GroupNorm(x)) materialised (the normalised input of an attention block).  One launch when the producer
     of x emitted its GroupNorm partial sums (``FUSE_GN_PROLOGUE``), else statistics / finalize + ``affine_act``."""
     _chk(x, "x")
@@ -389,8 +403,15 @@ def groupnorm_act(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torc
     if FUSE_GN_PROLOGUE and (one is not None or two is not None) and c % 4 == 0 and 2 * c + 2 * groups <= 12288:
         (pa, sa, ca), (pb, sb, cb) = (one, (None, 0, 0)) if one is not None else two
         if ca + cb == c:
-            out = torch.empty_like(x)
             L = _lib.lib()
+            if out_half:        # fp16 result: the only consumer is a tensor-core projection
+                outh = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+                _run("affine_act", dict(elems=x.numel(), fused_gn=1, f16out=1),
+                     lambda: L.afldm_affine_act_gn_f16out(x.data_ptr(), outh.data_ptr(), b, hw, c, ACT[act], pa.data_ptr(),
+                                                          sa, ca, _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma),
+                                                          _ptr(beta), _stream()), (x, outh, pa, pb, gamma, beta))
+                return outh
+            out = torch.empty_like(x)
             _run("affine_act", dict(elems=x.numel(), fused_gn=1),
                  lambda: L.afldm_affine_act_gn_f32(x.data_ptr(), out.data_ptr(), b, hw, c, ACT[act], pa.data_ptr(), sa, ca,
                                                    _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma), _ptr(beta),
@@ -491,9 +512,10 @@ def conv2d_f16out(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
     """fp16(conv(x) + bias) on the tcgen05 path (the q | k | v projection in front of ``attention_f16``).
     Returns None when this shape has no fp16 epilogue (split-K layers, shapes outside the tensor-core family):
     the caller then uses ``conv2d`` + ``attention``."""
-    _chk(w_packed, "w_packed")
-    if x.dtype != torch.float32 or not x.is_cuda:
-        raise _lib.AfldmError("conv2d_f16out: fp32 CUDA input expected")
+    if not x.is_cuda or x.dtype not in (torch.float32, torch.float16) or w_packed.dtype != x.dtype or \
+            not w_packed.is_contiguous():
+        raise _lib.AfldmError("conv2d_f16out: CUDA input and packed weight of one dtype (fp32 or fp16) expected")
+    f16in = x.dtype == torch.float16
     b, h, w_, cin = x.shape
     cout = w_packed.shape[0]
     x_pitch = _pitch(x)
@@ -501,23 +523,26 @@ def conv2d_f16out(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
     L = _lib.lib()
 
     def call():
-        return L.afldm_conv2d_f16out(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), out.data_ptr(), cout,
-                                     b, h, w_, cin, cout, ksize, _stream())
+        fn = L.afldm_conv2d_f16in_f16out if f16in else L.afldm_conv2d_f16out
+        return fn(x.data_ptr(), x_pitch, w_packed.data_ptr(), _ptr(bias), out.data_ptr(), cout,
+                  b, h, w_, cin, cout, ksize, _stream())
 
     code = call()
     if code == -3:
         return None
     _lib.check(code, "conv2d_f16out")
     if _recorder is not None:
-        _recorder.append(("conv2d_tf32", dict(B=b, H=h, W=w_, Cin=cin, Cout=cout, k=ksize, f16out=1,
+        _recorder.append(("conv2d_f16" if f16in else "conv2d_tf32",
+                          dict(B=b, H=h, W=w_, Cin=cin, Cout=cout, k=ksize, f16out=1,
                                               flops=2.0 * b * h * w_ * cout * cin * ksize * ksize), call,
                           (x, w_packed, bias, out)))
     return out
 
 
 def attention_f16(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``attention`` for fp16 q / k / v (column slices of the fp16 fused-QKV buffer); fp32 output."""
+                  out: Optional[torch.Tensor] = None, out_half: bool = False) -> torch.Tensor:
+    """``attention`` for fp16 q / k / v (column slices of the fp16 fused-QKV buffer); fp32 output, or fp16
+    (``out_half``) when a tensor-core projection is the only consumer."""
     b, nq, cd = q.shape
     bkv, nk, _ = k.shape
     d = cd // heads
@@ -529,11 +554,12 @@ def attention_f16(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
     if k.stride(1) != v.stride(1):
         raise _lib.AfldmError("attention_f16: k and v must share a pitch")
     if out is None:
-        out = torch.empty((b, nq, cd), dtype=torch.float32, device=q.device)
+        out = torch.empty((b, nq, cd), dtype=torch.float16 if out_half else torch.float32, device=q.device)
     L = _lib.lib()
+    fn = L.afldm_attention_f16_f16out if out.dtype == torch.float16 else L.afldm_attention_f16
     _run("attention_f16", dict(B=b, Nq=nq, Nk=nk, heads=heads, d=d, flops=4.0 * b * heads * nq * nk * d),
-         lambda: L.afldm_attention_f16(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1),
-                                       out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, _stream()),
+         lambda: fn(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1),
+                    out.data_ptr(), out.stride(1), b, bkv, nq, nk, heads, d, _stream()),
          (q, k, v, out))
     return out
 

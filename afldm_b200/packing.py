@@ -62,6 +62,18 @@ def fused_linear_params(owner: nn.Module, tag: str, layers: Sequence[nn.Module])
     return cache[1]
 
 
+def fused_linear_params_f16(owner: nn.Module, tag: str, layers: Sequence[nn.Module]):
+    """``fused_linear_params`` with the weight rounded to fp16 (B operand of the kind::f16 projection)."""
+    key = _key([t for m in layers for t in (m.weight, m.bias)])
+    name = "_afldm_fused_f16_" + tag
+    cache = getattr(owner, name, None)
+    if cache is None or cache[0] != key:
+        w, b = fused_linear_params(owner, tag, layers)
+        cache = (key, (w.to(torch.float16).contiguous(), b))
+        object.__setattr__(owner, name, cache)
+    return cache[1]
+
+
 def conv_params_padded(m: nn.Module, cin_pad: int) -> Tuple[torch.Tensor, Optional[torch.Tensor], int]:
     """``conv_params`` with the input channels zero-padded to ``cin_pad`` (conv_in: 4 latent channels -> one 32-channel
     TMA chunk, so the layer runs on the tensor-core path; the extra channels multiply zero weights)."""

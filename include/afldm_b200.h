@@ -109,6 +109,11 @@ AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W,
                         const float* scale, const float* shift, float* workspace,
                         size_t workspace_floats, afldm_stream_t stream);
 
+/* afldm_up2_ideal_f32 with an fp16 result (y: IEEE binary16 NHWC [B,2H,2W,C]): the up-sampled tensor is consumed only
+ * by the up-sampler's 3x3 convolution (af_blocks.py:99-104), see afldm_conv2d_f16in_f32.  Input planes up to 16 x 16
+ * (AFLDM_E_NOKERNEL above). */
+AFLDM_API int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, afldm_stream_t stream);
+
 /* LPF_RFFT(0.5)(x)[:, :, ::2, ::2] (afldm/af_modules/af_blocks.py:149-150):
  * x NHWC [B,2H,2W,C] -> y NHWC [B,H,W,C]  (H, W are the OUTPUT sizes). */
 AFLDM_API int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,
@@ -152,6 +157,13 @@ AFLDM_API int afldm_affine_act_gn_f32(const float* x, float* y, int B, int HW, i
                             const float* partial_a, int slots_a, int Ca, const float* partial_b,
                             int slots_b, int Cb, int groups, float eps, const float* gamma,
                             const float* beta, afldm_stream_t stream);
+
+/* afldm_affine_act_gn_f32 with an fp16 result (y: IEEE binary16 [B,HW,C]): the normalised attention input is consumed
+ * only by the q | k | v projection (afldm_conv2d_f16in_f16out). */
+AFLDM_API int afldm_affine_act_gn_f16out(const float* x, void* y, int B, int HW, int C, int act,
+                                         const float* partial_a, int slots_a, int Ca, const float* partial_b,
+                                         int slots_b, int Cb, int groups, float eps, const float* gamma,
+                                         const float* beta, afldm_stream_t stream);
 
 /* ---- convolution / linear as implicit GEMM -----------------------------------------------
  * nn.Conv2d(Cin, Cout, k, stride=1, padding=k/2) with k in {1,3} on NHWC input, fused epilogue:
@@ -208,6 +220,11 @@ AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, 
                                      float* workspace, size_t workspace_floats, float* gn_partial,
                                      afldm_stream_t stream);
 
+/* afldm_conv2d_f16out with fp16 operands as in afldm_conv2d_f16in_f32: y = fp16(conv(x) + bias), x, w, y binary16.
+ * The fused to_q | to_k | to_v projection between afldm_affine_act_gn_f16out and afldm_attention_f16. */
+AFLDM_API int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
+                                        int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
+
 /* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
  * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */
 AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float* bias, float* y,
@@ -233,6 +250,11 @@ AFLDM_API int afldm_attention_f32(const float* q, int q_pitch, const float* k, c
 AFLDM_API int afldm_attention_f16(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch,
                         float* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
                         afldm_stream_t stream);
+/* The same with an fp16 result (o: IEEE binary16, row pitch o_pitch halves): the attention output is consumed only by
+ * the to_out projection (afldm_conv2d_f16in_f32). */
+AFLDM_API int afldm_attention_f16_f16out(const void* q, int q_pitch, const void* k, const void* v, int kv_pitch,
+                               void* o, int o_pitch, int B, int Bkv, int Nq, int Nk, int heads, int d,
+                               afldm_stream_t stream);
 
 /* In-place row softmax: x[r][:] = softmax(scale * x[r][:]) over `cols` entries, row pitch `pitch`.
  * Used by the large-head-dim attention (VAE mid block: 1 head of 512) which runs as

@@ -166,3 +166,75 @@ def test_resnet_block_uses_f16_operands_and_stays_in_class():
         assert names.count("conv2d_f16") == 2, names
     err = (got - want).abs()
     assert err.max().item() < 2e-2 and err.mean().item() < 2e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("n,c", [(2, 768), (4, 768), (8, 384), (16, 384)])
+def test_up2_ideal_f16_store_is_rounded_f32_result(n, c):
+    x = nhwc(randn(3, c, n, n, seed=n))
+    f32 = ops.up2_ideal(x)
+    f16 = ops.up2_ideal(x, out_half=True)
+    assert f16.dtype == torch.float16 and f16.shape == f32.shape
+    assert torch.equal(f16, f32.half())
+
+
+def test_up2_ideal_f16_falls_back_to_f32_above_16():
+    x = nhwc(randn(1, 64, 32, 32, seed=1))
+    assert ops.up2_ideal(x, out_half=True).dtype == torch.float32
+
+
+@pytest.mark.parametrize("hw,c", [(1024, 192), (64, 384), (4, 768)])
+def test_groupnorm_act_f16_store(hw, c):
+    b, side = 4, int(hw ** 0.5)
+    x = nhwc(randn(b, 64, side, side, seed=hw))
+    y = ops.conv2d(x, ops.pack_conv_weight(randn(c, 64, 1, 1, seed=c) * 0.2), None, 1, algo="tf32", gn_stats=True)
+    if getattr(y, "_afldm_gn", None) is None:
+        pytest.skip("no GroupNorm partial sums for this shape")
+    gamma, beta = randn(c, seed=5) * 0.2 + 1, randn(c, seed=6) * 0.2
+    f32 = ops.groupnorm_act(y, 32, 1e-5, gamma, beta, act="identity")
+    f16 = ops.groupnorm_act(y, 32, 1e-5, gamma, beta, act="identity", out_half=True)
+    assert f16.dtype == torch.float16
+    assert torch.equal(f16, f32.half())
+
+
+def test_attention_f16_output_and_f16_projection():
+    """q | k | v projection with fp16 operands and fp16 result, attention with an fp16 result: each equals the fp32-result
+    form rounded to nearest fp16 (attention) / agrees with the TF32-operand projection within the class bound."""
+    b, n, c, heads = 16, 16, 384, 16
+    xn = nhwc(randn(b, c, n, n, seed=1))
+    w = randn(3 * c, c, seed=2) * (1.0 / c ** 0.5)
+    bias = randn(3 * c, seed=3) * 0.1
+    qkv32 = ops.conv2d_f16out(xn, w.contiguous(), bias, 1)
+    qkv16 = ops.conv2d_f16out(xn.half(), w.half().contiguous(), bias, 1)
+    assert qkv32 is not None and qkv16 is not None and qkv16.dtype == torch.float16
+    want = (xn.half().double() @ w.half().double().t() + bias.double()).float()
+    torch.testing.assert_close(qkv16.float(), want, rtol=2e-3, atol=2e-3)       # fp16 result rounding + fp32 sums
+    err = (qkv16.float() - qkv32.float()).abs()
+    assert err.max().item() < 1.5e-2 and err.mean().item() < 1.5e-3
+    qkv = qkv16.view(b, n * n, 3 * c)
+    q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
+    o32 = ops.attention_f16(q, k, v, heads)
+    o16 = ops.attention_f16(q, k, v, heads, out_half=True)
+    assert o16.dtype == torch.float16
+    assert torch.equal(o16, o32.half())
+
+
+def test_attention_block_f16_chain_stays_in_class():
+    from afldm_b200.models.blocks import Attention
+    torch.manual_seed(0)
+    att = Attention(384, 16, 24).to(DEV).eval()
+    x = nhwc(randn(16, 64, 16, 16, seed=1))
+    pre = ops.conv2d(x, ops.pack_conv_weight(randn(384, 64, 1, 1, seed=3) * 0.2), None, 1, algo="tf32", gn_stats=True)
+    rec = []
+    with torch.no_grad():
+        ops.record_to(rec)
+        try:
+            got = att(ops.nchw_view(pre))
+        finally:
+            ops.record_to(None)
+        ops.set_default_conv_algo("simt")
+        want = att(ops.nchw_view(pre.clone()))
+    names = [r[0] for r in rec]
+    if ops.F16_CONV and ops.F16_ATTENTION:
+        assert names == ["affine_act", "conv2d_f16", "attention_f16", "conv2d_f16"], names
+    err = (got - want).abs()
+    assert err.max().item() < 2e-2 and err.mean().item() < 2e-3, (err.max().item(), err.mean().item())
