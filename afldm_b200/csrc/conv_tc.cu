@@ -847,7 +847,9 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks, bool f16 = false)
         // of the step on B200 (profiles/r01_conv_splitk_sweep.md): -0.12 ms per step against "two waves, >= 4 stages".
         s = std::max(1, num_sms() / tiles);                // floor: tiles * s CTAs never spill into a second,
                                                            // nearly empty wave (160 CTAs on 148 SMs = 2x the time)
-        s = std::min(s, std::max(1, p.total_iters / 8));
+        // (fp16 operands: a stage carries twice the K, so ">= 4 stages" keeps the split sizes of the swept TF32 rule -
+        // and with them the split-K reduce that emits the GroupNorm sums of the 4x4 / 2x2 levels)
+        s = std::min(s, std::max(1, p.total_iters / (f16 ? 4 : 8)));
         s = std::min(s, 64);
         if (ks == 1 && tiles >= 32) s = 1;
     }
