@@ -25,6 +25,18 @@ for _ in range(3):
         x3 = r(16, 32, 32, 384)
         w3 = ops.pack_conv_weight(r(384, 384, 3, 3) * 0.02)
         ops.conv2d(x3, w3, r(384), 3, algo="tf32")
+    if which in ("conv16",):
+        # the same three layers with fp16 operands (tcgen05.mma.kind::f16), as the resnets / the up-sampler run them
+        x = r(16, 32, 32, 192).half()
+        w = ops.pack_conv_weight(r(192, 192, 3, 3) * 0.02).half()
+        ops.set_default_conv_algo("tf32")
+        ops.conv2d(x, w, r(192), 3, residual=r(16, 32, 32, 192), gn_stats=True)
+        x2 = r(16, 16, 16, 384).half()
+        w2 = ops.pack_conv_weight(r(384, 384, 3, 3) * 0.02).half()
+        ops.conv2d(x2, w2, r(384), 3, gn_stats=True)
+        x3 = r(16, 32, 32, 384).half()
+        w3 = ops.pack_conv_weight(r(384, 384, 3, 3) * 0.02).half()
+        ops.conv2d(x3, w3, r(384), 3)
     if which in ("all", "attn"):
         qkv = r(16, 1024, 576)
         ops.attention(qkv[:, :, :192], qkv[:, :, 192:384], qkv[:, :, 384:], 8, algo="tf32")
