@@ -32,7 +32,9 @@ SIGNATURES = {
     "afldm_filtered_act_gn_f16out": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
     "afldm_filtered_act_gn_cat_f16out": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _f, _p, _p, _p]),
     "afldm_up2_ideal_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "afldm_up2_ideal_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "afldm_up2_ideal_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "afldm_filtered_act_f16out": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "afldm_affine_act_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "afldm_lpf_down2_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
     "afldm_lpf_down2_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "afldm_groupnorm_scratch_floats": (_sz, [_i, _i, _i]),

@@ -130,7 +130,7 @@ gn_finalize_kernel(const float2* __restrict__ pa, int slots_a, int Ca, const flo
 template <int ACT>
 __global__ void __launch_bounds__(256)
 affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long long n4, int C4,
-                  long long per_image4, const float4* __restrict__ scale, const float4* __restrict__ shift) {
+                  long long per_image4, const float4* __restrict__ scale, const float4* __restrict__ shift, int y_half) {
     pdl_trigger();
     pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -149,7 +149,15 @@ affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
         v.y = apply_act<ACT>(v.y);
         v.z = apply_act<ACT>(v.z);
         v.w = apply_act<ACT>(v.w);
-        y[i] = v;
+        if (y_half) {
+            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(y)[i] = pk;
+        } else {
+            y[i] = v;
+        }
     }
 }
 
@@ -277,8 +285,8 @@ extern "C" int afldm_groupnorm_finalize_f32(const float* partial_a, int slots_a,
     return launched();
 }
 
-extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,
-                                    const float* scale, const float* shift, afldm_stream_t stream) {
+static int affine_act_impl(const float* x, float* y, int y_half, int B, int HW, int C, int act,
+                           const float* scale, const float* shift, afldm_stream_t stream) {
     if (x == nullptr || y == nullptr || B <= 0 || HW <= 0 || C <= 0) return AFLDM_E_ARG;
     if ((scale == nullptr) != (shift == nullptr)) return AFLDM_E_ARG;
     if (C % 4 != 0) return AFLDM_E_SHAPE;
@@ -291,13 +299,24 @@ extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int
     auto sh = reinterpret_cast<const float4*>(shift);
     if (act == AFLDM_ACT_SILU)
         launch_k(affine_act_kernel<AFLDM_ACT_SILU>, dim3(blocks), dim3(256), 0, st, 
-            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh);
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh, y_half);
     else if (act == AFLDM_ACT_IDENTITY)
         launch_k(affine_act_kernel<AFLDM_ACT_IDENTITY>, dim3(blocks), dim3(256), 0, st, 
-            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh);
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n4, C / 4, per_image4, sc, sh, y_half);
     else
         return AFLDM_E_ARG;
     return launched();
+}
+
+extern "C" int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,
+                                    const float* scale, const float* shift, afldm_stream_t stream) {
+    return affine_act_impl(x, y, 0, B, HW, C, act, scale, shift, stream);
+}
+
+extern "C" int afldm_affine_act_f16out(const float* x, void* y, int B, int HW, int C, int act,
+                                       const float* scale, const float* shift, afldm_stream_t stream) {
+    if (static_cast<const void*>(x) == y) return AFLDM_E_ARG;
+    return affine_act_impl(x, static_cast<float*>(y), 1, B, HW, C, act, scale, shift, stream);
 }
 
 static int affine_act_gn_impl(const float* x, float* y, int y_half, int B, int HW, int C, int act,

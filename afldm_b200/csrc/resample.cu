@@ -417,7 +417,17 @@ resample_phased_kernel(const float* __restrict__ x, float* __restrict__ y, int C
                     continue;
                 }
                 if constexpr (MODE == MODE_UP2) {
-                    float* yp = y + ((size_t)(b * M) * M + line) * C + c0 + c;
+                    const size_t yo = ((size_t)(b * M) * M + line) * C + c0 + c;
+                    if (af.y_half) {
+                        __half* yh = reinterpret_cast<__half*>(y) + yo;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            yh[(size_t)(2 * i) * M * C] = __float2half_rn(apply_act<ACT>(xr[i]));
+                            yh[(size_t)(2 * i + 1) * M * C] = __float2half_rn(apply_act<ACT>(od[i]));
+                        }
+                        continue;
+                    }
+                    float* yp = y + yo;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         yp[(size_t)(2 * i) * M * C] = apply_act<ACT>(xr[i]);
@@ -762,7 +772,8 @@ int dispatch_n(const float* x, float* y, int B, int n, int C, const Affine& af, 
             if (n == 16) return launch_fact_mma<16, ACT>(x, y, B, C, af, st);
         }
     }
-    if (af.y_half && (MODE == MODE_DOWN2 || n >= 32)) return AFLDM_E_NOKERNEL;   // fp16 stores: fact_mma + n <= 16 kernels
+    // fp16 stores: fact_mma (n = 16, 32), the register-resident kernels (n <= 16) and the phased up-sampler (n = 32)
+    if (af.y_half && (MODE == MODE_DOWN2 || (n >= 32 && MODE != MODE_UP2))) return AFLDM_E_NOKERNEL;
     switch (n) {
         case 2: return launch_one<2, 32, MODE, ACT>(x, y, B, C, af, st);
         case 4: return launch_one<4, 32, MODE, ACT>(x, y, B, C, af, st);
@@ -861,14 +872,33 @@ extern "C" int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W
     return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, y, B, H, C, plain_affine(scale, shift), st);
 }
 
-extern "C" int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, afldm_stream_t stream) {
+extern "C" int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, float* workspace,
+                                      size_t workspace_floats, afldm_stream_t stream) {
     if (bad_args(x, static_cast<const float*>(y), B, H, W, C, nullptr, nullptr) || static_cast<const void*>(x) == y)
         return AFLDM_E_ARG;
     if (H != W) return AFLDM_E_SHAPE;
-    if (H > 16) return AFLDM_E_NOKERNEL;      // fp16 stores live in the register-resident kernels (n <= 16)
+    cudaStream_t st = as_stream(stream);
+    if (H > 32)
+        return resample_large(MODE_UP2, AFLDM_ACT_IDENTITY, x, static_cast<float*>(y), B, H, C, nullptr, nullptr, workspace,
+                              workspace_floats, st, 1);
     Affine af = plain_affine(nullptr, nullptr);
     af.y_half = 1;
-    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, static_cast<float*>(y), B, H, C, af, as_stream(stream));
+    return dispatch_n<MODE_UP2, AFLDM_ACT_IDENTITY>(x, static_cast<float*>(y), B, H, C, af, st);
+}
+
+extern "C" int afldm_filtered_act_f16out(const float* x, void* y, int B, int H, int W, int C, int act,
+                                         const float* scale, const float* shift, float* workspace,
+                                         size_t workspace_floats, afldm_stream_t stream) {
+    float* yf = static_cast<float*>(y);
+    if (bad_args(x, yf, B, H, W, C, scale, shift) || static_cast<const void*>(x) == y) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
+    if (H != W) return AFLDM_E_SHAPE;
+    cudaStream_t st = as_stream(stream);
+    if (H > 32) return resample_large(MODE_FACT, act, x, yf, B, H, C, scale, shift, workspace, workspace_floats, st, 1);
+    Affine af = plain_affine(scale, shift);
+    af.y_half = 1;
+    if (act == AFLDM_ACT_SILU) return dispatch_n<MODE_FACT, AFLDM_ACT_SILU>(x, yf, B, H, C, af, st);
+    return dispatch_n<MODE_FACT, AFLDM_ACT_IDENTITY>(x, yf, B, H, C, af, st);
 }
 
 extern "C" int afldm_lpf_down2_f32(const float* x, float* y, int B, int H, int W, int C, float* workspace,

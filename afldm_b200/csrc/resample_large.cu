@@ -67,6 +67,7 @@ struct LineArgs {
     long long in_outer, in_inner, in_pos;      // element strides: line = outer * n_inner + inner
     long long out_outer, out_inner, out_pos;
     int n_inner, n_lines, C, lines_per_image;  // lines_per_image: lines sharing one batch index (for scale/shift)
+    int y_half;                                // y holds IEEE binary16 (same element strides); tensor-core passes only
 };
 
 // N: SMALL length (input of UP / UPACTDOWN, output of DOWN).  CTA = 32 channels x L lines.
@@ -260,6 +261,7 @@ line_mma_kernel(const LineArgs a) {
     constexpr int NT = N / 8, KS = N / 16;
     const float* xin[2];
     float* yout[2];
+    __half* youth[2];                                // the same positions when y holds fp16 (a.y_half)
     bool ok[2];
     float sc[2] = {1.f, 1.f}, sh[2] = {0.f, 0.f};
 #pragma unroll
@@ -269,6 +271,7 @@ line_mma_kernel(const LineArgs a) {
         const int outer = line / a.n_inner, inner = line - outer * a.n_inner;
         xin[r] = a.x + outer * a.in_outer + inner * a.in_inner + ch;
         yout[r] = a.y + outer * a.out_outer + inner * a.out_inner + ch;
+        youth[r] = reinterpret_cast<__half*>(a.y) + outer * a.out_outer + inner * a.out_inner + ch;
         if (a.scale != nullptr) {
             const int b = line / a.lines_per_image;
             sc[r] = a.scale[(size_t)b * a.C + ch];
@@ -302,8 +305,13 @@ line_mma_kernel(const LineArgs a) {
                 lm_split(v0, v1, ah[ks][idx], al[ks][idx]);
                 if constexpr (OP == OP_UP) {
                     if (ok[r]) {
-                        yout[r][(size_t)(2 * j) * a.out_pos] = apply_act<ACT>(v0);
-                        yout[r][(size_t)(2 * j + 2) * a.out_pos] = apply_act<ACT>(v1);
+                        if (a.y_half) {
+                            youth[r][(size_t)(2 * j) * a.out_pos] = __float2half_rn(apply_act<ACT>(v0));
+                            youth[r][(size_t)(2 * j + 2) * a.out_pos] = __float2half_rn(apply_act<ACT>(v1));
+                        } else {
+                            yout[r][(size_t)(2 * j) * a.out_pos] = apply_act<ACT>(v0);
+                            yout[r][(size_t)(2 * j + 2) * a.out_pos] = apply_act<ACT>(v1);
+                        }
                     }
                 } else {
                     etile[j * LM_EP + g + 8 * r] = apply_act<ACT>(v0);
@@ -326,8 +334,13 @@ line_mma_kernel(const LineArgs a) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         if (ok[r]) {
-                            yout[r][(size_t)(2 * j + 1) * a.out_pos] = apply_act<ACT>(acc[c][2 * r]);
-                            yout[r][(size_t)(2 * j + 3) * a.out_pos] = apply_act<ACT>(acc[c][2 * r + 1]);
+                            if (a.y_half) {
+                                youth[r][(size_t)(2 * j + 1) * a.out_pos] = __float2half_rn(apply_act<ACT>(acc[c][2 * r]));
+                                youth[r][(size_t)(2 * j + 3) * a.out_pos] = __float2half_rn(apply_act<ACT>(acc[c][2 * r + 1]));
+                            } else {
+                                yout[r][(size_t)(2 * j + 1) * a.out_pos] = apply_act<ACT>(acc[c][2 * r]);
+                                yout[r][(size_t)(2 * j + 3) * a.out_pos] = apply_act<ACT>(acc[c][2 * r + 1]);
+                            }
                         }
                     }
                 } else {
@@ -412,8 +425,13 @@ line_mma_kernel(const LineArgs a) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 if (ok[r]) {
-                    yout[r][(size_t)j * a.out_pos] = acc[c][2 * r];
-                    yout[r][(size_t)(j + 1) * a.out_pos] = acc[c][2 * r + 1];
+                    if (a.y_half) {
+                        youth[r][(size_t)j * a.out_pos] = __float2half_rn(acc[c][2 * r]);
+                        youth[r][(size_t)(j + 1) * a.out_pos] = __float2half_rn(acc[c][2 * r + 1]);
+                    } else {
+                        yout[r][(size_t)j * a.out_pos] = acc[c][2 * r];
+                        yout[r][(size_t)(j + 1) * a.out_pos] = acc[c][2 * r + 1];
+                    }
                 }
             }
         }
@@ -443,12 +461,13 @@ bool large_mma_enabled() {
 template <int N, int OP, int ACT>
 int launch_pass(const LineArgs& a, cudaStream_t st) {
     if (large_mma_enabled() && a.C % 8 == 0) return launch_lines_mma<N, OP, ACT>(a, st);
+    if (a.y_half) return AFLDM_E_NOKERNEL;          // fp16 stores live in the tensor-core passes
     return launch_lines<N, OP, ACT>(a, st);
 }
 
 template <int N>
 int run_large(int mode, int act, const float* x, float* y, int B, int C, const float* scale, const float* shift,
-              float* ws, cudaStream_t st) {
+              float* ws, cudaStream_t st, int y_half) {
     // mode: 0 filtered act, 1 up2, 2 down2 (the enum of resample.cu)
     const size_t plane2 = (size_t)B * N * 2 * N * C;   // [B][N][2N][C] intermediate
     int rc = 0, launches = 0;
@@ -463,7 +482,9 @@ int run_large(int mode, int act, const float* x, float* y, int B, int C, const f
         rc = (act == AFLDM_ACT_SILU) ? launch_pass<N, OP_UPACTDOWN, AFLDM_ACT_SILU>(cmid, st)
                                      : launch_pass<N, OP_UPACTDOWN, AFLDM_ACT_IDENTITY>(cmid, st);
         if (rc) return rc;
-        rc = launch_pass<N, OP_DOWN, AFLDM_ACT_IDENTITY>(rows(y1, y, B, N, 2 * N, N, C), st);
+        LineArgs last = rows(y1, y, B, N, 2 * N, N, C);
+        last.y_half = y_half;                         // only the pass that writes the result
+        rc = launch_pass<N, OP_DOWN, AFLDM_ACT_IDENTITY>(last, st);
         launches = 3;
     } else if (mode == 1) {
         float* t1 = ws;
@@ -471,12 +492,15 @@ int run_large(int mode, int act, const float* x, float* y, int B, int C, const f
         r.scale = scale; r.shift = shift;
         rc = launch_pass<N, OP_UP, AFLDM_ACT_IDENTITY>(r, st);
         if (rc) return rc;
-        rc = launch_pass<N, OP_UP, AFLDM_ACT_IDENTITY>(cols(t1, y, B, N, 2 * N, 2 * N, C), st);
+        LineArgs last = cols(t1, y, B, N, 2 * N, 2 * N, C);
+        last.y_half = y_half;
+        rc = launch_pass<N, OP_UP, AFLDM_ACT_IDENTITY>(last, st);
         launches = 2;
     } else {
         float* y1 = ws;
         rc = launch_pass<N, OP_DOWN, AFLDM_ACT_IDENTITY>(cols(x, y1, B, 2 * N, N, 2 * N, C), st);
         if (rc) return rc;
+        if (y_half) return AFLDM_E_NOKERNEL;
         rc = launch_pass<N, OP_DOWN, AFLDM_ACT_IDENTITY>(rows(y1, y, B, N, 2 * N, N, C), st);
         launches = 2;
     }
@@ -493,12 +517,13 @@ size_t resample_large_workspace_floats(int mode, int B, int n, int C) {
 }
 
 int resample_large(int mode, int act, const float* x, float* y, int B, int n, int C, const float* scale,
-                   const float* shift, float* ws, size_t ws_floats, cudaStream_t st) {
+                   const float* shift, float* ws, size_t ws_floats, cudaStream_t st, int y_half) {
     if (n != 64 && n != 128) return AFLDM_E_NOKERNEL;
+    if (y_half && !(large_mma_enabled() && C % 8 == 0)) return AFLDM_E_NOKERNEL;   // before any pass is launched
     if (C % 32 != 0) return AFLDM_E_SHAPE;
     if (ws == nullptr || ws_floats < resample_large_workspace_floats(mode, B, n, C)) return AFLDM_E_WORKSPACE;
-    if (n == 64) return run_large<64>(mode, act, x, y, B, C, scale, shift, ws, st);
-    return run_large<128>(mode, act, x, y, B, C, scale, shift, ws, st);
+    if (n == 64) return run_large<64>(mode, act, x, y, B, C, scale, shift, ws, st, y_half);
+    return run_large<128>(mode, act, x, y, B, C, scale, shift, ws, st, y_half);
 }
 
 }  // namespace afldm

@@ -29,7 +29,8 @@ def norm_act(x: torch.Tensor, norm: nn.GroupNorm, nonlinearity: nn.Module, out_h
     if isinstance(nonlinearity, WarpedNonlinearity):
         return ops.filtered_act_groupnorm(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=nonlinearity.act,
                                           out_half=out_half)
-    return ops.groupnorm_act(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=act_name(nonlinearity))
+    return ops.groupnorm_act(x, norm.num_groups, norm.eps, norm.weight, norm.bias, act=act_name(nonlinearity),
+                             out_half=out_half)
 
 
 def conv_after_act(a: torch.Tensor, conv: nn.Module, **kw) -> torch.Tensor:

@@ -150,15 +150,30 @@ def to_nchw_contiguous(y: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------- ideal resampling
 def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
-                 act: str = "silu", out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """WarpedNonlinearity (af_blocks.py:19-28) on NHWC x, optional folded GroupNorm affine."""
+                 act: str = "silu", out: Optional[torch.Tensor] = None, out_half: bool = False) -> torch.Tensor:
+    """WarpedNonlinearity (af_blocks.py:19-28) on NHWC x, optional folded GroupNorm affine.  ``out_half``: the result
+    MAY be fp16 (a tensor-core convolution is its only consumer); fp32 where the library has no fp16 store."""
     _chk(x, "x")
     b, h, w, c = x.shape
-    if out is None:
-        out = torch.empty_like(x)
     L = _lib.lib()
     need = L.afldm_resample_workspace_floats(0, b, h, w, c)
     ws = scratch(x.device, need) if need else None
+    if out_half and out is None:
+        outh = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+
+        def call_h():
+            return L.afldm_filtered_act_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, ACT[act],
+                                               _ptr(scale), _ptr(shift), _ptr(ws), need, _stream())
+
+        code = call_h()
+        if code != -3:
+            _lib.check(code, "filtered_act_f16out")
+            if _recorder is not None:
+                _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h,
+                                  (x, outh, scale, shift, ws)))
+            return outh
+    if out is None:
+        out = torch.empty_like(x)
     _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel()),
          lambda: L.afldm_filtered_act_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act],
                                           _ptr(scale), _ptr(shift), _ptr(ws), need, _stream()),
@@ -293,7 +308,7 @@ def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Opti
                                                      _ptr(beta), _stream()), (x, out, pa, pb, gamma, beta))
             return out
     scale, shift = groupnorm_affine(x, groups, eps, gamma, beta)
-    return filtered_act(x, scale, shift, act=act)
+    return filtered_act(x, scale, shift, act=act, out_half=out_half)
 
 
 def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
@@ -302,18 +317,20 @@ def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
     for a tensor-core convolution as the only consumer)."""
     _chk(x, "x")
     b, h, w, c = x.shape
-    if out_half and scale is None and h == w and h <= 16:
+    if out_half and scale is None and h == w:
         outh = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
         Lh = _lib.lib()
+        needh = Lh.afldm_resample_workspace_floats(1, b, h, w, c)
+        wsh = scratch(x.device, needh) if needh else None
 
         def call_h():
-            return Lh.afldm_up2_ideal_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, _stream())
+            return Lh.afldm_up2_ideal_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, _ptr(wsh), needh, _stream())
 
         code = call_h()
         if code != -3:
             _lib.check(code, "up2_ideal_f16out")
             if _recorder is not None:
-                _recorder.append(("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h, (x, outh)))
+                _recorder.append(("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h, (x, outh, wsh)))
             return outh
     out = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
     L = _lib.lib()
@@ -379,13 +396,19 @@ def groupnorm_affine(x: torch.Tensor, groups: int, eps: float, gamma: Optional[t
 
 
 def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
-               act: str = "silu", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               act: str = "silu", out: Optional[torch.Tensor] = None, out_half: bool = False) -> torch.Tensor:
     _chk(x, "x")
     b, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (b * c)
+    L = _lib.lib()
+    if out_half and out is None:
+        outh = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        _run("affine_act", dict(elems=x.numel(), f16out=1),
+             lambda: L.afldm_affine_act_f16out(x.data_ptr(), outh.data_ptr(), b, hw, c, ACT[act], _ptr(scale), _ptr(shift),
+                                               _stream()), (x, outh, scale, shift))
+        return outh
     if out is None:
         out = torch.empty_like(x)
-    L = _lib.lib()
     _run("affine_act", dict(elems=x.numel()),
          lambda: L.afldm_affine_act_f32(x.data_ptr(), out.data_ptr(), b, hw, c, ACT[act], _ptr(scale), _ptr(shift),
                                         _stream()), (x, out, scale, shift))
@@ -418,7 +441,7 @@ def groupnorm_act(x: torch.Tensor, groups: int, eps: float, gamma: Optional[torc
                                                    _stream()), (x, out, pa, pb, gamma, beta))
             return out
     scale, shift = groupnorm_affine(x, groups, eps, gamma, beta)
-    return affine_act(x, scale, shift, act=act)
+    return affine_act(x, scale, shift, act=act, out_half=out_half and c % 4 == 0)
 
 
 # ------------------------------------------------------------------------- conv / linear

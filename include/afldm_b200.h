@@ -73,6 +73,13 @@ AFLDM_API int afldm_filtered_act_f32(const float* x, float* y, int B, int H, int
                            const float* scale, const float* shift, float* workspace,
                            size_t workspace_floats, afldm_stream_t stream);
 
+/* afldm_filtered_act_f32 with an fp16 result (y: IEEE binary16 NHWC; no in-place form): see
+ * afldm_filtered_act_gn_f16out below for why.  AFLDM_E_NOKERNEL where only an exact-FMA kernel applies
+ * (AFLDM_FACT_MMA=0 at n >= 32). */
+AFLDM_API int afldm_filtered_act_f16out(const float* x, void* y, int B, int H, int W, int C, int act,
+                                        const float* scale, const float* shift, float* workspace,
+                                        size_t workspace_floats, afldm_stream_t stream);
+
 /* The same with the GroupNorm finalised inside the kernel from the partial sums the producer of x emitted
  * (afldm_conv2d_f32 gn_partial; channels [0,Ca) from partial_a, [Ca,Ca+Cb) from partial_b as in
  * afldm_groupnorm_finalize_f32): GroupNorm -> filtered activation costs ONE launch and one pass over x.
@@ -110,9 +117,10 @@ AFLDM_API int afldm_up2_ideal_f32(const float* x, float* y, int B, int H, int W,
                         size_t workspace_floats, afldm_stream_t stream);
 
 /* afldm_up2_ideal_f32 with an fp16 result (y: IEEE binary16 NHWC [B,2H,2W,C]): the up-sampled tensor is consumed only
- * by the up-sampler's 3x3 convolution (af_blocks.py:99-104), see afldm_conv2d_f16in_f32.  Input planes up to 16 x 16
- * (AFLDM_E_NOKERNEL above). */
-AFLDM_API int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, afldm_stream_t stream);
+ * by the up-sampler's 3x3 convolution (af_blocks.py:99-104), see afldm_conv2d_f16in_f32.  workspace as in
+ * afldm_up2_ideal_f32 (planes of 64 / 128; AFLDM_E_NOKERNEL there when the exact-FMA line passes are selected). */
+AFLDM_API int afldm_up2_ideal_f16out(const float* x, void* y, int B, int H, int W, int C, float* workspace,
+                                     size_t workspace_floats, afldm_stream_t stream);
 
 /* LPF_RFFT(0.5)(x)[:, :, ::2, ::2] (afldm/af_modules/af_blocks.py:149-150):
  * x NHWC [B,2H,2W,C] -> y NHWC [B,H,W,C]  (H, W are the OUTPUT sizes). */
@@ -149,6 +157,11 @@ AFLDM_API int afldm_groupnorm_finalize_f32(const float* partial_a, int slots_a, 
  * normalised input of an attention block). scale/shift may be NULL. x may alias y. */
 AFLDM_API int afldm_affine_act_f32(const float* x, float* y, int B, int HW, int C, int act,
                          const float* scale, const float* shift, afldm_stream_t stream);
+
+/* afldm_affine_act_f32 with an fp16 result (y: IEEE binary16 [B,HW,C]; no in-place form): plain SiLU(GroupNorm(x))
+ * in front of a tensor-core convolution (VAE blocks without the filtered activation). */
+AFLDM_API int afldm_affine_act_f16out(const float* x, void* y, int B, int HW, int C, int act,
+                                      const float* scale, const float* shift, afldm_stream_t stream);
 
 /* GroupNorm (finalised from the producer's partial sums, as in afldm_groupnorm_finalize_f32) and
  * y = act(x*scale + shift) in one launch: the normalised input of an attention block

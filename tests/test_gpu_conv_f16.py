@@ -168,18 +168,33 @@ def test_resnet_block_uses_f16_operands_and_stays_in_class():
     assert err.max().item() < 2e-2 and err.mean().item() < 2e-3, (err.max().item(), err.mean().item())
 
 
-@pytest.mark.parametrize("n,c", [(2, 768), (4, 768), (8, 384), (16, 384)])
+@pytest.mark.parametrize("n,c", [(2, 768), (4, 768), (8, 384), (16, 384), (32, 64), (64, 64), (128, 32)])
 def test_up2_ideal_f16_store_is_rounded_f32_result(n, c):
-    x = nhwc(randn(3, c, n, n, seed=n))
+    x = nhwc(randn(3 if n <= 32 else 1, c, n, n, seed=n))
     f32 = ops.up2_ideal(x)
     f16 = ops.up2_ideal(x, out_half=True)
     assert f16.dtype == torch.float16 and f16.shape == f32.shape
     assert torch.equal(f16, f32.half())
 
 
-def test_up2_ideal_f16_falls_back_to_f32_above_16():
-    x = nhwc(randn(1, 64, 32, 32, seed=1))
-    assert ops.up2_ideal(x, out_half=True).dtype == torch.float32
+@pytest.mark.parametrize("n,c", [(8, 64), (16, 64), (32, 64), (64, 64), (128, 32)])
+def test_filtered_act_plain_f16_store(n, c):
+    """afldm_filtered_act_f16out (explicit scale / shift; the three line passes for planes of 64 / 128)."""
+    b = 2
+    x = nhwc(randn(b, c, n, n, seed=n))
+    sc, sh = randn(b, c, seed=1) * 0.1 + 1, randn(b, c, seed=2) * 0.1
+    f32 = ops.filtered_act(x, sc, sh)
+    f16 = ops.filtered_act(x, sc, sh, out_half=True)
+    assert f16.dtype == torch.float16
+    assert torch.equal(f16, f32.half())
+
+
+def test_affine_act_plain_f16_store():
+    x = nhwc(randn(2, 128, 64, 64, seed=3))
+    sc, sh = randn(2, 128, seed=1) * 0.1 + 1, randn(2, 128, seed=2) * 0.1
+    f32 = ops.affine_act(x, sc, sh, act="silu")
+    f16 = ops.affine_act(x, sc, sh, act="silu", out_half=True)
+    assert f16.dtype == torch.float16 and torch.equal(f16, f32.half())
 
 
 @pytest.mark.parametrize("hw,c", [(1024, 192), (64, 384), (4, 768)])
