@@ -70,22 +70,37 @@ class ResnetBlock2D(nn.Module):
         half1 = ops.conv_f16_supported(bsz, hh, ww, cin_total, self.out_channels)
         half2 = ops.conv_f16_supported(bsz, hh, ww, self.out_channels, self.out_channels)
         act1, sc = None, None
+        xs = ops.nhwc(skip) if skip is not None else None
+        warped = isinstance(self.nonlinearity, WarpedNonlinearity)
+        # conv_shortcut reads the block input only and is consumed by conv2's epilogue: issue it first, on a side stream
+        # (a parallel graph branch under norm1 / activation / conv1), with its own split-K scratch buffer
+        main = side = None
+        if self.conv_shortcut is not None and ops.SHORTCUT_SIDE_STREAM and x.is_cuda and (skip is None or warped):
+            main, side = torch.cuda.current_stream(x.device), ops.side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.scratch_slot(ops.SIDE_SCRATCH_SLOT):
+                ws, bs, ks = conv_params(self.conv_shortcut)
+                sc = ops.conv2d_cat(x, xs, ws, bs, ks) if skip is not None else ops.conv2d(x, ws, bs, ks)
         if skip is not None:
-            xs = ops.nhwc(skip)
-            if isinstance(self.nonlinearity, WarpedNonlinearity) and self.conv_shortcut is not None:
+            if warped and self.conv_shortcut is not None and (sc is not None or side is None):
                 n1 = self.norm1
                 act1 = ops.filtered_act_groupnorm_cat(x, xs, n1.num_groups, n1.eps, n1.weight, n1.bias,
                                                       act=self.nonlinearity.act, out_half=half1)
-                if act1 is not None:
+                if act1 is not None and sc is None:
                     ws, bs, ks = conv_params(self.conv_shortcut)
                     sc = ops.conv2d_cat(x, xs, ws, bs, ks)
             if act1 is None or sc is None:
+                if side is not None:
+                    main.wait_stream(side)          # a shortcut already issued for the un-concatenated input is dropped
+                    side = None
                 x = ops.concat_channels(x, xs)
-                act1 = None
+                act1, sc = None, None
         if act1 is None:
             act1 = norm_act(x, self.norm1, self.nonlinearity, out_half=half1)
         h = conv_after_act(act1, self.conv1, row_add=temb_proj, gn_stats=True)
         a = norm_act(h, self.norm2, self.nonlinearity, out_half=half2)
+        if side is not None:
+            main.wait_stream(side)
         if sc is not None:
             out = conv_after_act(a, self.conv2, residual=sc, out=sc, gn_stats=True)
         elif self.conv_shortcut is not None:

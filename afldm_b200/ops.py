@@ -108,6 +108,23 @@ def scratch(device: torch.device, nfloats: int) -> torch.Tensor:
     return buf
 
 
+_side_streams = {}
+# conv_shortcut of a resnet on a side stream (a parallel branch of the captured step graph): it depends on the block
+# input only and is needed by conv2's epilogue, so it runs under norm1 / activation / conv1 instead of between them
+SHORTCUT_SIDE_STREAM = os.environ.get("AFLDM_SC_SIDE", "1") == "1"
+SIDE_SCRATCH_SLOT = 2
+
+
+def side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One auxiliary stream per (device, calling stream) for work that is independent of the main dependency chain."""
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=idx)
+    return st
+
+
 # ------------------------------------------------------------------------- layout
 def nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical [B,C,H,W] -> physical [B,H,W,C] contiguous (zero-copy for channels_last input)."""
