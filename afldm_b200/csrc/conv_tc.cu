@@ -849,7 +849,8 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks, bool f16 = false)
                                                            // nearly empty wave (160 CTAs on 148 SMs = 2x the time)
         // (fp16 operands: a stage carries twice the K, so ">= 4 stages" keeps the split sizes of the swept TF32 rule -
         // and with them the split-K reduce that emits the GroupNorm sums of the 4x4 / 2x2 levels)
-        s = std::min(s, std::max(1, p.total_iters / (f16 ? 4 : 8)));
+        static const int f16_min_iters = getenv("AFLDM_TC_F16_MINIT") ? std::max(1, atoi(getenv("AFLDM_TC_F16_MINIT"))) : 4;
+        s = std::min(s, std::max(1, p.total_iters / (f16 ? f16_min_iters : 8)));
         s = std::min(s, 64);
         if (ks == 1 && tiles >= 32) s = 1;
     }
