@@ -353,6 +353,88 @@ extern "C" int afldm_upfirdn2d_f32(const float* x, const float* f, float* y, int
     return launched();
 }
 
+// ------------------------------------------------------------------ separable plane operator (NCHW)
+// y[p] = My . x[p] . Mx^T for every plane p: the fused form of ImageShifter('ideal' | 'ideal_crop', r).shift
+// (afldm/shift_utils/shifters.py:157-191): ideal r-fold up-sampling, circular roll by round(t r), validity mask and
+// [::r, ::r] decimation are all linear and separable, so per axis they collapse into ONE n x n matrix
+// S[i][j] = d_r[((i - j) r - s) mod n r] (rows of masked positions zeroed) that the host builds in fp64
+// (afldm_b200/shift_utils/shifters.py).  The r-fold up-sampled tensor (64x the data at r = 8) never exists, and a
+// sweep of shifts is one launch pair: plane p uses matrix pair p / planes_per_matrix.
+// Two passes of a 32 x 32-tiled fp32 GEMM with sequential k order (deterministic): C[r][c] = sum_k A[r][k] B(k, c),
+// B stored [c][k] (BT: the row pass, Mx) or [k][c] (the column pass reads the row pass's result).
+namespace afldm {
+namespace {
+template <bool BT>
+__global__ void __launch_bounds__(256)
+sep_gemm_kernel(const float* __restrict__ A, long long a_plane, long long a_matrix, const float* __restrict__ Bm,
+                long long b_plane, long long b_matrix, float* __restrict__ Cm, int R, int Cc, int K,
+                int planes_per_matrix) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float As[32][33], Bs[32][33];
+    const int p = blockIdx.z, m = p / planes_per_matrix;
+    const float* a = A + (size_t)p * a_plane + (size_t)m * a_matrix;
+    const float* b = Bm + (size_t)p * b_plane + (size_t)m * b_matrix;
+    float* c = Cm + (size_t)p * R * Cc;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = ty + 8 * u;
+            const int ar = r0 + rr, ak = k0 + tx;
+            As[rr][tx] = (ar < R && ak < K) ? a[(size_t)ar * K + ak] : 0.f;
+            if (BT) {       // B(k, c) = b[c][k]: tile rows = c, columns = k
+                const int bc = c0 + rr, bk = k0 + tx;
+                Bs[rr][tx] = (bc < Cc && bk < K) ? b[(size_t)bc * K + bk] : 0.f;
+            } else {        // B(k, c) = b[k][c]: tile rows = k, columns = c
+                const int bk = k0 + rr, bc = c0 + tx;
+                Bs[rr][tx] = (bk < K && bc < Cc) ? b[(size_t)bk * Cc + bc] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const float bv = BT ? Bs[tx][kk] : Bs[kk][tx];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(As[ty + 8 * u][kk], bv, acc[u]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int rr = r0 + ty + 8 * u, cc = c0 + tx;
+        if (rr < R && cc < Cc) c[(size_t)rr * Cc + cc] = acc[u];
+    }
+}
+}  // namespace
+}  // namespace afldm
+
+extern "C" size_t afldm_plane_sep_transform_workspace_floats(int planes, int Hin, int Wout) {
+    if (planes <= 0 || Hin <= 0 || Wout <= 0) return 0;
+    return (size_t)planes * Hin * Wout;
+}
+
+extern "C" int afldm_plane_sep_transform_f32(const float* x, const float* my, const float* mx, float* y,
+                                             float* workspace, size_t workspace_floats, int planes,
+                                             int planes_per_matrix, int Hin, int Win, int Hout, int Wout,
+                                             afldm_stream_t stream) {
+    if (x == nullptr || my == nullptr || mx == nullptr || y == nullptr || x == y) return AFLDM_E_ARG;
+    if (planes <= 0 || planes_per_matrix <= 0 || Hin <= 0 || Win <= 0 || Hout <= 0 || Wout <= 0) return AFLDM_E_ARG;
+    if (planes > 65535) return AFLDM_E_SHAPE;
+    if (workspace == nullptr || workspace_floats < (size_t)planes * Hin * Wout) return AFLDM_E_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    // rows: T[p] (Hin x Wout) = x[p] (Hin x Win) . Mx[m]^T, Mx stored [Wout][Win]
+    launch_k(sep_gemm_kernel<true>, dim3(ceil_div(Wout, 32), ceil_div(Hin, 32), planes), dim3(256), 0, st,
+             x, (long long)Hin * Win, 0LL, mx, 0LL, (long long)Wout * Win, workspace, Hin, Wout, Win, planes_per_matrix);
+    // columns: y[p] (Hout x Wout) = My[m] (Hout x Hin) . T[p]
+    launch_k(sep_gemm_kernel<false>, dim3(ceil_div(Wout, 32), ceil_div(Hout, 32), planes), dim3(256), 0, st,
+             my, 0LL, (long long)Hout * Hin, (const float*)workspace, (long long)Hin * Wout, 0LL, y, Hout, Wout, Hin,
+             planes_per_matrix);
+    return launched(2);
+}
+
 extern "C" int afldm_pad_channels_f32(const float* x, int C, float* y, int Cpad, long long pixels, afldm_stream_t stream) {
     if (x == nullptr || y == nullptr || C <= 0 || Cpad < C || pixels <= 0 || x == y) return AFLDM_E_ARG;
     const long long total = pixels * Cpad;

@@ -238,6 +238,20 @@ AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, 
 AFLDM_API int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
                                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
 
+/* ---- fractional shift (the equivariance measurement's warp) ---------------------------------
+ * ImageShifter('ideal' | 'ideal_crop', r).shift(img, ti, tj) (afldm/shift_utils/shifters.py:157-191):
+ * UpsampleRFFT(r) -> torch.roll by (round(ti r), round(tj r)) -> validity mask (gen_valid_mask :31-49) ->
+ * [::r, ::r].  Every step is linear and separable, so per axis the chain is one matrix and the whole warp is
+ *   y[p] = My[m] . x[p] . Mx[m]^T            per NCHW plane p, m = p / planes_per_matrix
+ * with My [n_mat][Hout][Hin], Mx [n_mat][Wout][Win] built by the caller (fp64 -> fp32; afldm_b200/shift_utils).
+ * A sweep of shifts of one image is ONE call (planes = shifts x channels), and the r-fold up-sampled tensor is never
+ * materialised.  workspace: afldm_plane_sep_transform_workspace_floats(planes, Hin, Wout) floats. */
+AFLDM_API size_t afldm_plane_sep_transform_workspace_floats(int planes, int Hin, int Wout);
+AFLDM_API int afldm_plane_sep_transform_f32(const float* x, const float* my, const float* mx, float* y,
+                                            float* workspace, size_t workspace_floats, int planes,
+                                            int planes_per_matrix, int Hin, int Win, int Hout, int Wout,
+                                            afldm_stream_t stream);
+
 /* nn.Linear on a few rows (time embedding MLP, time_emb_proj): y[M,N] = act_in(x[M,K]) w[N,K]^T + b.
  * act_in applies SiLU to x on load (ResnetBlock2D: time_emb_proj(nonlinearity(temb))). M <= 64. */
 AFLDM_API int afldm_linear_rows_f32(const float* x, const float* w, const float* bias, float* y,
