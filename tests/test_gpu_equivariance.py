@@ -6,6 +6,7 @@ STORE (reference trajectory) / LOAD (shifted trajectories) mode, exact-fp32 kern
 import pytest
 import torch
 
+from afldm_b200.shift_utils import ImageShifter
 from afldm_b200 import ops
 from afldm_b200.af_modules import af_api
 from afldm_b200.models import UNet2DModel
@@ -63,7 +64,8 @@ def test_shift_equivariance_metric_matches_oracle(algo, tol_db, tol_traj):
             torch.testing.assert_close(base_m, base_r, rtol=0, atol=tol_traj)
             st_r.to_load()
             st_m.to_load()
-            psnr_r, psnr_m = [], []
+            psnr_r, psnr_m, psnr_d = [], [], []
+            dev_shifter = ImageShifter("ideal_crop", 8)
             for k in (1, 4):                       # shifts of k/8 latent pixels (scripts: offsets i/8)
                 tj = k / 8.0
                 shifted, mask = OS.ideal_shift(init, 0.0, tj, 8, crop=True)
@@ -73,9 +75,16 @@ def test_shift_equivariance_metric_matches_oracle(algo, tol_db, tol_traj):
                 out_m = _denoise(mine, DDIMScheduler.from_config(), st_m, shifted, False)
                 psnr_r.append(float(OS.mask_psnr(out_r, want_r, mask)))
                 psnr_m.append(float(OS.mask_psnr(out_m, want_m, mask)))
+                # the same measurement with the warps on device too (afldm_b200.shift_utils: one fused operator per axis)
+                shifted_d, mask_d = dev_shifter.shift(init, 0.0, tj)
+                want_d, _ = dev_shifter.shift(base_m, 0.0, tj)
+                out_d = _denoise(mine, DDIMScheduler.from_config(), st_m, shifted_d, False)
+                psnr_d.append(float(OS.mask_psnr(out_d, want_d, mask_d)))
         print(f"masked shift-PSNR (dB) [{algo}]  oracle:", [round(p, 3) for p in psnr_r], " cuda:", [round(p, 3) for p in psnr_m])
-        for pr, pm in zip(psnr_r, psnr_m):
+        print("   with on-device shifters:", [round(p, 3) for p in psnr_d])
+        for pr, pm, pd in zip(psnr_r, psnr_m, psnr_d):
             assert abs(pr - pm) < tol_db, (psnr_r, psnr_m)
+            assert abs(pr - pd) < tol_db, (psnr_r, psnr_d)
     finally:
         ops.set_default_conv_algo(prev_algo)
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
