@@ -14,7 +14,8 @@ import torch.nn.functional as F
 
 from afldm_b200 import ops
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ops.F16_CONV, reason="fp16 operand storage switched off (AFLDM_CONV_F16=0)")]
 DEV = "cuda"
 
 
