@@ -1096,13 +1096,18 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
         cfg.blockDim = dim3(TC_THREADS);
         cfg.dynamicSmemBytes = p.smem_bytes;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        // programmatic dependent launch for the CTA-pair launches too (they were the only kernels of the step launched
+        // fully serialised; AFLDM_PDL_PAIRS=0 restores that)
+        static const bool pdl_pairs = !(getenv("AFLDM_PDL_PAIRS") && atoi(getenv("AFLDM_PDL_PAIRS")) == 0);
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (pdl_enabled() && pdl_pairs) ? 2 : 1;
         if (p.halo) {
             if (f16) (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, true>, map_a, map_a2, map_b, a);
             else (void)cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, false>, map_a, map_a2, map_b, a);
