@@ -31,6 +31,14 @@ extern "C" size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, in
     return p.splitk > 1 ? (size_t)p.splitk * p.M * Cout : 0;
 }
 
+extern "C" int afldm_conv2d_supported(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
+    if (algo == AFLDM_CONV_SIMT_F32) return 1;
+    if (algo == AFLDM_CONV_TCGEN05_TF32 || algo == AFLDM_CONV_TCGEN05_F16)
+        return conv_tc_supported(B, H, W, Cin, Cout, ksize, algo == AFLDM_CONV_TCGEN05_F16) ? 1 : 0;
+    return 0;
+}
+
 extern "C" int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
     if (algo != AFLDM_CONV_TCGEN05_TF32 && algo != AFLDM_CONV_TCGEN05_F16) return 0;

@@ -976,6 +976,10 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks, int x_half)
     return (HW == 64 || HW == 32) ? 1 : 0;               // tiles of whole images aligned to the epilogue's row quarters
 }
 
+bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int ks, int x_half) {
+    return tc_plan(B, H, W, Cin, Cout, ks, x_half != 0).ok;
+}
+
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats, int x_half) {
     const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks, x_half != 0);
     if (!p.ok) return false;

@@ -133,7 +133,7 @@ class AttnProcessor2_0:
         # ... and then the normalised input and the attention output, each consumed by ONE projection, are stored as
         # fp16 too (kind::f16 projections: half the operand bytes)
         half = (f16 and encoder_hidden_states is None and attn.group_norm is not None
-                and ops.conv_f16_supported(b, h, w, c, 3 * c))
+                and ops.conv_f16_supported(b, h, w, c, 3 * c, 1) and ops.conv_f16_supported(b, h, w, c, c, 1))
         xn = x
         if attn.group_norm is not None:
             gn = attn.group_norm

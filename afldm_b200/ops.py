@@ -201,13 +201,13 @@ def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: O
 FUSE_CONCAT = os.environ.get("AFLDM_FUSE_CONCAT", "1") == "1"
 
 
-def conv_f16_supported(b: int, h: int, w: int, cin: int, cout: int) -> bool:
-    """Shapes ``conv2d`` accepts with fp16 operands (mirrors the tcgen05 plan of csrc/conv_tc.cu with 64-channel
-    stages); the producer of the activation asks this BEFORE it decides to emit fp16."""
-    def pow2(v):
-        return v > 0 and (v & (v - 1)) == 0
-    return (F16_CONV and _default_conv_algo == "tf32" and cin % 64 == 0 and cout >= 16 and cout % 16 == 0
-            and pow2(h) and pow2(w) and (w <= 128 or w % 128 == 0) and b * h * w >= 1)
+def conv_f16_supported(b: int, h: int, w: int, cin: int, cout: int, ksize: int = 3) -> bool:
+    """Whether ``conv2d`` will accept this layer with fp16 operands (TF32 class, switch on, and the tcgen05 plan of
+    csrc/conv_tc.cu covers the shape with 64-channel stages - ``afldm_conv2d_supported``, a host-side query).  The
+    producer of the activation asks this BEFORE it decides to store fp16."""
+    if not (F16_CONV and _default_conv_algo == "tf32"):
+        return False
+    return bool(_lib.lib().afldm_conv2d_supported(b, h, w, cin, cout, ksize, 2))
 
 
 def filtered_act_groupnorm_cat(a: torch.Tensor, b: torch.Tensor, groups: int, eps: float, gamma: Optional[torch.Tensor],

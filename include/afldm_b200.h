@@ -197,6 +197,9 @@ AFLDM_API int afldm_affine_act_gn_f16out(const float* x, void* y, int B, int HW,
  *       layer's norm then needs no pass over y); slots = afldm_conv2d_gn_slots(...), 0 = not available
  *       for this shape / algo (then gn_partial must be NULL). */
 AFLDM_API int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
+/* 1 when `algo` has a kernel for this shape (host-side plan only, no launch): a producer asks this before it decides to
+ * store an activation as fp16 for afldm_conv2d_f16in_f32 (algo = AFLDM_CONV_TCGEN05_F16). */
+AFLDM_API int afldm_conv2d_supported(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
                      const float* row_add, int row_add_pitch, const float* residual, int res_pitch,

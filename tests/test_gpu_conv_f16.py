@@ -56,7 +56,7 @@ F16_CASES = [  # B, H, W, Cin, Cout, k: the resnet conv1 / conv2 shapes of the F
 
 @pytest.mark.parametrize("b,h,w,cin,cout,k", F16_CASES)
 def test_conv2d_f16_operands_vs_fp64(b, h, w, cin, cout, k):
-    assert ops.conv_f16_supported(b, h, w, cin, cout)
+    assert ops.conv_f16_supported(b, h, w, cin, cout, k)
     x = randn(b, cin, h, w, seed=cin + h)
     wt = randn(cout, cin, k, k, seed=cout) * (1.0 / (cin * k * k) ** 0.5)
     bias, row, res = randn(cout, seed=3), randn(b, cout, seed=4), randn(b, cout, h, w, seed=5)

@@ -171,3 +171,49 @@ def test_i2sb_schedule_matches_oracle():
     ts = torch.tensor([10, 700])
     torch.testing.assert_close(mine.add_noise(x, x1, ts, is_ode=True), ref.add_noise(x, x1, ts, is_ode=True))
     torch.testing.assert_close(mine.compute_label(ts, x, x1), ref.compute_label(ts, x, x1))
+
+
+# ------------------------------------------------------------------------- fp16 operand storage: host-side decisions
+def test_conv_plan_query_for_fp16_operands():
+    """afldm_conv2d_supported is a host-side plan query (no GPU): fp16 operands need 64-channel stages."""
+    from afldm_b200 import _lib
+    L = _lib.lib()
+    assert L.afldm_conv2d_supported(16, 32, 32, 192, 192, 3, 2) == 1        # resnet conv at the 32x32 level
+    assert L.afldm_conv2d_supported(16, 2, 2, 1536, 768, 3, 2) == 1         # split-K level
+    assert L.afldm_conv2d_supported(16, 32, 32, 32, 192, 3, 2) == 0         # padded conv_in: 32 channels = half a stage
+    assert L.afldm_conv2d_supported(16, 32, 32, 32, 192, 3, 1) == 1         # ... which the TF32 instantiation takes
+    assert L.afldm_conv2d_supported(16, 32, 32, 4, 192, 3, 1) == 0          # raw latents: SIMT only
+    assert L.afldm_conv2d_supported(16, 32, 32, 4, 192, 3, 0) == 1
+    assert L.afldm_conv2d_supported(16, 24, 24, 192, 192, 3, 2) == 0        # non-power-of-two plane
+    assert L.afldm_conv2d_supported(0, 32, 32, 192, 192, 3, 2) == 0
+    # the workspace / slot queries accept the fp16 algo id
+    assert L.afldm_conv2d_workspace_floats(16, 2, 2, 1536, 768, 3, 2) > 0
+    assert L.afldm_conv2d_gn_slots(16, 32, 32, 192, 192, 3, 2) == 8
+
+
+def test_conv_f16_supported_follows_class_and_switch():
+    from afldm_b200 import ops
+    prev = ops.default_conv_algo()
+    try:
+        ops.set_default_conv_algo("simt")
+        assert not ops.conv_f16_supported(16, 32, 32, 192, 192, 3)           # exact-fp32 class never stores fp16
+        ops.set_default_conv_algo("tf32")
+        assert ops.conv_f16_supported(16, 32, 32, 192, 192, 3) == ops.F16_CONV
+        assert not ops.conv_f16_supported(16, 32, 32, 96, 192, 3)
+    finally:
+        ops.set_default_conv_algo(prev)
+
+
+def test_fp16_weight_pack_is_cached_and_invalidated():
+    import torch
+    from afldm_b200.packing import conv_params, conv_params_f16
+    conv = torch.nn.Conv2d(64, 32, 3, padding=1)
+    w16, b16, k = conv_params_f16(conv)
+    w32, _, _ = conv_params(conv)
+    assert w16.dtype == torch.float16 and w16.shape == (32, 9, 64) and k == 3
+    assert torch.equal(w16, w32.half())
+    assert conv_params_f16(conv)[0] is w16                                   # cached
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                                # in-place update bumps the version
+    w16b = conv_params_f16(conv)[0]
+    assert w16b is not w16 and torch.equal(w16b, conv_params(conv)[0].half())
