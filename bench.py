@@ -381,6 +381,10 @@ def main():
             a["flops"] += count * meta.get("flops", 0.0)
             if name == "filtered_act":
                 a["bytes"] += count * 8.0 * meta["elems"]
+                # tensor work of the separable-GEMM form on mma.m16n8k16 (3-term fp16 split): 36 n FLOP per element
+                # for the planes that run on the tensor-core kernels (n = 16, 32), DESIGN.md section 6
+                if meta.get("N") in (16, 32):
+                    a["mma_flops"] = a.get("mma_flops", 0.0) + count * 36.0 * meta["N"] * meta["elems"]
             elif name == "up2_ideal":
                 a["bytes"] += count * 20.0 * meta["elems"]
             elif name == "lpf_down2":
@@ -418,6 +422,13 @@ def main():
             ach = fa["bytes"] / (fa["ms"] / 1e3) / 1e9
             fir = {"kernel": "filtered_act", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                    "frac": ach / pk["hbm"], "launches_per_step": fa["launches"], "ms_per_step": fa["ms"]}
+            if fa.get("mma_flops"):
+                # second ceiling of the formulation actually run: the warp-level tensor path (measured mma.sync fp16 rate,
+                # profiles/r01_mma_sync_rates.txt) - at n = 32 it, not HBM, is the nearer floor
+                tf = fa["mma_flops"] / (fa["ms"] / 1e3) / 1e12
+                fir["tensor_ceiling"] = {"flops_per_step": fa["mma_flops"], "achieved": tf, "peak": 553.6, "unit": "TFLOP/s",
+                                         "frac": tf / 553.6,
+                                         "peak_source": "measured mma.sync.m16n8k16 f16 rate on B200 (profiles/r01_mma_sync_rates.txt)"}
 
     # ---- BASELINE config #3 (reported beside the headline, not part of it): alias-free VAE decode
     vae_decode = None
