@@ -528,7 +528,10 @@ __device__ __forceinline__ void make_circ(CircB<N>& f, int g, int t) {
 
 // acc[nt][.] += sum_j in[.][j] F[(i - j) mod N] for the 16 lines of the warp; `in` is in accumulator layout:
 // in[r][nt][e] = line (g + 8 r), position 8 nt + 2 t + e.
-template <int N>
+// TERMS = 3: x F ~ xh Fh + xl Fh + xh Fl (22 significant bits per operand: fp32 accuracy, the default);
+// TERMS = 2: xh (Fh + Fl) - exact filter, operand rounded to 11 bits; TERMS = 1: xh Fh - the plain TF32-class product
+// (opt-in experiments, AFLDM_FACT_TERMS).
+template <int N, int TERMS>
 __device__ __forceinline__ void circ_mma(const float (&in)[2][N / 8][2], const CircB<N>& f, float (&acc)[N / 8][4]) {
     uint32_t ah[N / 16][4], al[N / 16][4];
 #pragma unroll
@@ -536,12 +539,18 @@ __device__ __forceinline__ void circ_mma(const float (&in)[2][N / 8][2], const C
 #pragma unroll
         for (int idx = 0; idx < 4; ++idx) {
             const int r = idx & 1, nt = 2 * ks + (idx >> 1);
-            split_pack(in[r][nt][0], in[r][nt][1], ah[ks][idx], al[ks][idx]);
+            if constexpr (TERMS == 3) {
+                split_pack(in[r][nt][0], in[r][nt][1], ah[ks][idx], al[ks][idx]);
+            } else {
+                const __half2 h = __floats2half2_rn(in[r][nt][0], in[r][nt][1]);
+                ah[ks][idx] = *reinterpret_cast<const uint32_t*>(&h);
+                al[ks][idx] = 0u;
+            }
         }
     }
     // consecutive MMAs go to different accumulators (N/8 independent chains); small terms first
 #pragma unroll
-    for (int term = 0; term < 3; ++term) {
+    for (int term = 3 - TERMS; term < 3; ++term) {
 #pragma unroll
         for (int ks = 0; ks < N / 16; ++ks) {
 #pragma unroll
@@ -557,7 +566,7 @@ __device__ __forceinline__ void circ_mma(const float (&in)[2][N / 8][2], const C
 
 // y = down-sample of the line whose even samples are e[] and odd samples o[] (both activated):
 // y[i] = e[i] / 2 - (-1)^i altsum(e) / (2N) + sum_m G[i - m] o[m]
-template <int N>
+template <int N, int TERMS>
 __device__ __forceinline__ void down_mma(const float (&e)[2][N / 8][2], const float (&o)[2][N / 8][2],
                                          const CircB<N>& fd, float (&acc)[N / 8][4]) {
     float s[2];
@@ -577,10 +586,10 @@ __device__ __forceinline__ void down_mma(const float (&e)[2][N / 8][2], const fl
         acc[nt][2] = fmaf(0.5f, e[1][nt][0], -s[1]);
         acc[nt][3] = fmaf(0.5f, e[1][nt][1], s[1]);
     }
-    circ_mma<N>(o, fd, acc);
+    circ_mma<N, TERMS>(o, fd, acc);
 }
 
-template <int N, int ACT>
+template <int N, int ACT, int TERMS>
 __global__ void __launch_bounds__(FM_THREADS, 2)
 fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const Affine af) {
     pdl_trigger();
@@ -642,7 +651,7 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
         float acc[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        circ_mma<N>(e, fu, acc);
+        circ_mma<N, TERMS>(e, fu, acc);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -670,7 +679,7 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
             float acc[NT][4];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-            circ_mma<N>(e, fu, acc);
+            circ_mma<N, TERMS>(e, fu, acc);
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -682,7 +691,7 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
                     }
         }
         float acc[NT][4];
-        down_mma<N>(e, o, fd, acc);
+        down_mma<N, TERMS>(e, o, fd, acc);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -707,7 +716,7 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
                     o[r][nt][q] = tp[8];
                 }
         float acc[NT][4];
-        down_mma<N>(e, o, fd, acc);
+        down_mma<N, TERMS>(e, o, fd, acc);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const size_t yo = ((size_t)(b * N + i0 + r) * N) * C + c0 + g;
@@ -728,9 +737,9 @@ fact_mma_kernel(const float* __restrict__ x, float* __restrict__ y, int C, const
     }
 }
 
-template <int N, int ACT>
-int launch_fact_mma(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
-    auto kern = fact_mma_kernel<N, ACT>;
+template <int N, int ACT, int TERMS>
+int launch_fact_mma_t(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
+    auto kern = fact_mma_kernel<N, ACT, TERMS>;
     constexpr int smem = FmTile<N>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
@@ -740,6 +749,15 @@ int launch_fact_mma(const float* x, float* y, int B, int C, const Affine& af, cu
     }
     launch_k(kern, dim3(C / FM_CG, B), dim3(FM_THREADS), smem, st, x, y, C, af);
     return launched();
+}
+
+template <int N, int ACT>
+int launch_fact_mma(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
+    // split terms per product: 3 = fp32 accuracy (default); 1 / 2 only when the result is stored as fp16 anyway
+    static const int terms = getenv("AFLDM_FACT_TERMS") ? atoi(getenv("AFLDM_FACT_TERMS")) : 3;
+    if (af.y_half && terms == 1) return launch_fact_mma_t<N, ACT, 1>(x, y, B, C, af, st);
+    if (af.y_half && terms == 2) return launch_fact_mma_t<N, ACT, 2>(x, y, B, C, af, st);
+    return launch_fact_mma_t<N, ACT, 3>(x, y, B, C, af, st);
 }
 
 bool fact_mma_enabled() {
