@@ -161,7 +161,7 @@ class UNet2DModel(nn.Module):
         else:
             w, b, k = conv_params(self.conv_in)
             h = ops.nchw_view(ops.conv2d(x, w, b, k))
-        main.wait_stream(side)
+        ops.defer_join(main, side)      # joined by the first op that reads a projection row (first resnet's conv1)
         skips = (h,)
         pi = 0
         for blk in self.down_blocks:
@@ -177,6 +177,7 @@ class UNet2DModel(nn.Module):
             pi += n
             skips = skips[:-n]
 
+        ops.join_deferred()             # no-op unless no resnet consumed a projection row
         hx = ops.nhwc(h)
         gn = self.conv_norm_out
         a = ops.groupnorm_act(hx, gn.num_groups, gn.eps, gn.weight, gn.bias, act=act_name(self.conv_act))   # conv_act is NOT wrapped

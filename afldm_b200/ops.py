@@ -125,6 +125,25 @@ def side_stream(dev: torch.device) -> "torch.cuda.Stream":
     return st
 
 
+_deferred_join = None
+
+
+def defer_join(main: "torch.cuda.Stream", side: "torch.cuda.Stream") -> None:
+    """``main`` must wait for ``side`` before the NEXT op that consumes a time-embedding projection row (``conv2d`` with
+    ``row_add``, ``linear_rows``) - not earlier: the time-embedding branch (~70 us on its side stream) then also runs
+    under the first resnet's GroupNorm + filtered activation instead of stalling the main stream right after conv_in."""
+    global _deferred_join
+    _deferred_join = (main, side)
+
+
+def join_deferred() -> None:
+    global _deferred_join
+    if _deferred_join is not None:
+        main, side = _deferred_join
+        _deferred_join = None
+        main.wait_stream(side)
+
+
 # ------------------------------------------------------------------------- layout
 def nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical [B,C,H,W] -> physical [B,H,W,C] contiguous (zero-copy for channels_last input)."""
@@ -478,6 +497,8 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     (tensor-core path), attached to the returned tensor for ``groupnorm_affine`` to pick up.  ``x``, ``residual`` and ``out`` may be channel slices of
     wider NHWC buffers (last-dim stride 1, pixel pitch = stride(-2))."""
     L = _lib.lib()
+    if row_add is not None:
+        join_deferred()
     b, h, w_, cin = x.shape
     cout = w_packed.shape[0]
     if x.stride(-1) != 1 or not x.is_cuda or x.dtype not in (torch.float32, torch.float16):
@@ -620,6 +641,8 @@ def _pitch(t: torch.Tensor) -> int:
 def linear_rows(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act_in: str = "identity",
                 act_out: str = "identity") -> torch.Tensor:
     """y = act_out(act_in(x) @ w.T + bias) for a few rows (time-embedding MLP)."""
+    if _deferred_join is not None and torch.cuda.current_stream(x.device) == _deferred_join[0]:
+        join_deferred()          # a resnet projecting the embedding itself, on the main stream
     _chk(x, "x")
     _chk(w, "w")
     m, k = x.shape
