@@ -2,6 +2,8 @@
 // embedding, channel concat, NCHW <-> NHWC, the DDIM update, and StyleGAN3's upfirdn2d.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace afldm {
@@ -253,6 +255,69 @@ inline int grid_for(long long n, int threads = 256, int cap = 148 * 8) {
     return (int)std::max<long long>(1, std::min<long long>(cap, (n + threads - 1) / threads));
 }
 
+
+// K = 768 (the time-embedding width of the FFHQ UNet: Linear(768, 768) and the 27 fused time_emb_proj rows,
+// 768 -> 14016), M <= 16.  The projection is a 43 MB weight stream; the generic kernel above keeps one 64-byte load
+// per row in flight per lane and reached 1.1 TB/s.  Here a warp owns TWO output columns and every lane issues its whole
+// share of both weight rows up front (12 independent 128-bit loads = 6 KB in flight per warp), then runs the 16 x 2
+// dot products out of registers against the staged activations: the stream is bandwidth-, not latency-bound.
+constexpr int L768_K4 = 192, L768_IT = 6, L768_NR = 2, L768_M = 16;
+
+template <int ACT_IN, int ACT_OUT>
+__global__ void __launch_bounds__(256)
+linear_rows_k768_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        float* __restrict__ y, int M, int N) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ float4 xs4[];  // [M][192], activated
+    for (int i = threadIdx.x; i < M * L768_K4; i += blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        v.x = apply_act<ACT_IN>(v.x); v.y = apply_act<ACT_IN>(v.y);
+        v.z = apply_act<ACT_IN>(v.z); v.w = apply_act<ACT_IN>(v.w);
+        xs4[i] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int tasks = (N + L768_NR - 1) / L768_NR;
+    for (int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < tasks; task += gridDim.x * warps_per_block) {
+        const int n0 = task * L768_NR;
+        float4 wv[L768_NR][L768_IT];
+#pragma unroll
+        for (int r = 0; r < L768_NR; ++r) {
+            const float4* wr = reinterpret_cast<const float4*>(w + (size_t)min(n0 + r, N - 1) * (4 * L768_K4));
+#pragma unroll
+            for (int j = 0; j < L768_IT; ++j) wv[r][j] = __ldg(wr + lane + 32 * j);
+        }
+        float acc[L768_NR][L768_M];
+#pragma unroll
+        for (int i = 0; i < L768_M; ++i) {
+            const float4* xr = xs4 + min(i, M - 1) * L768_K4 + lane;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < L768_IT; ++j) {
+                const float4 xv = xr[32 * j];
+                a0 = fmaf(xv.x, wv[0][j].x, a0); a0 = fmaf(xv.y, wv[0][j].y, a0);
+                a0 = fmaf(xv.z, wv[0][j].z, a0); a0 = fmaf(xv.w, wv[0][j].w, a0);
+                a1 = fmaf(xv.x, wv[1][j].x, a1); a1 = fmaf(xv.y, wv[1][j].y, a1);
+                a1 = fmaf(xv.z, wv[1][j].z, a1); a1 = fmaf(xv.w, wv[1][j].w, a1);
+            }
+            acc[0][i] = a0;
+            acc[1][i] = a1;
+        }
+#pragma unroll
+        for (int r = 0; r < L768_NR; ++r) {
+#pragma unroll
+            for (int i = 0; i < L768_M; ++i) {
+                const float sum = warp_sum(acc[r][i]);
+                if (lane == 0 && i < M && n0 + r < N) {
+                    const float v = sum + (bias != nullptr ? bias[n0 + r] : 0.f);
+                    y[(size_t)i * N + n0 + r] = apply_act<ACT_OUT>(v);
+                }
+            }
+        }
+    }
+}
 }  // namespace
 }  // namespace afldm
 
@@ -267,8 +332,22 @@ extern "C" int afldm_linear_rows_f32(const float* x, const float* w, const float
     cudaStream_t st = as_stream(stream);
     const bool vec = (K % 4 == 0) && aligned16(x) && aligned16(w);
     const int blocks = vec ? std::min(ceil_div(ceil_div(N, LIN_NR), 8), 148 * 2) : std::min(ceil_div(N, 8), 148 * 4);
+    static const bool k768 = !(getenv("AFLDM_LIN_K768") && atoi(getenv("AFLDM_LIN_K768")) == 0);
+    const bool fast768 = vec && k768 && K == 4 * L768_K4 && M <= L768_M;
+    const int blocks768 = std::min(ceil_div(ceil_div(N, L768_NR), 8), 148 * 2);
 #define AFLDM_LIN(AI, AO)                                                                              \
     {                                                                                                  \
+        if (fast768) {                                                                                 \
+            static bool cfg768 = false;                                                                \
+            if (!cfg768) {                                                                             \
+                cudaError_t e = cudaFuncSetAttribute(linear_rows_k768_kernel<AI, AO>,                  \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+                if (e != cudaSuccess) return (int)e;                                                   \
+                cfg768 = true;                                                                         \
+            }                                                                                          \
+            launch_k(linear_rows_k768_kernel<AI, AO>, dim3(blocks768), dim3(256), smem, st, x, w, bias, y, M, N); \
+            return launched();                                                                         \
+        }                                                                                              \
         auto kern = vec ? linear_rows_vec_kernel<AI, AO> : linear_rows_kernel<AI, AO>;                 \
         if (smem > 48 * 1024) {                                                                        \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
