@@ -1,5 +1,5 @@
 // tcgen05 implicit-GEMM convolution (k = 1 / 3, stride 1, "same" padding) for sm_100a:
-// TF32 operands from shared memory, fp32 accumulators in TMEM, operands staged by TMA.
+// TF32 or fp16 operands from shared memory, fp32 accumulators in TMEM, operands staged by TMA.
 //
 // GEMM view: D[M = B*H*W pixels][N = Cout] = A[M][K] * W[N][K]^T, K = taps * Cin, k = tap*Cin + ci.
 //
@@ -19,6 +19,12 @@
 //
 // Numeric class: TF32 (10-bit mantissa) products, fp32 accumulation - the same class as the
 // reference's default cuDNN path (torch.backends.cudnn.allow_tf32 = True).
+//
+// F16 instantiation (x_half): activations and packed weights arrive as IEEE fp16 (the same 11 significant bits, stored
+// by the producing kernel - DESIGN.md section 2); a 128-byte stage row then holds 64 channels, tcgen05.mma.kind::f16
+// retires K = 16 per instruction, and everything measured in BYTES (ring, swizzle atoms, descriptors, halo boxes) is
+// unchanged: the same kernel runs half the stages per layer on half the operand bytes.  Accumulators, epilogue
+// and outputs stay fp32.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
