@@ -34,6 +34,7 @@ SIGNATURES = {
     "afldm_up2_ideal_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "afldm_up2_ideal_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
     "afldm_filtered_act_f16out": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "afldm_filtered_act_tc": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "afldm_affine_act_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "afldm_lpf_down2_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _sz, _p]),
     "afldm_lpf_down2_gn_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),

@@ -14,10 +14,12 @@ from __future__ import annotations
 
 from typing import Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
 from .. import ops
+from ..af_libs.ideal_lpf import sep_transform
 from ..af_modules.af_blocks import WarpedNonlinearity, act_name
 from ..packing import conv_params, conv_params_f16, fused_linear_params, fused_linear_params_f16
 
@@ -203,10 +205,17 @@ class Attention(nn.Module):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states, **kwargs)
 
 
+def _decimate2(x_nchw: torch.Tensor, phase: int) -> torch.Tensor:
+    """x[:, :, phase::2, phase::2] as a selection operator on ``afldm_plane_sep_transform_f32``."""
+    h, w = x_nchw.shape[-2:]
+    sel_h = np.eye(h)[phase::2][: h // 2]
+    sel_w = np.eye(w)[phase::2][: w // 2]
+    return sep_transform(x_nchw, sel_h, sel_w)
+
+
 class Downsample2D(nn.Module):
     """diffusers Downsample2D (3x3 conv, stride 2).  Holds the weights that
-    ``replace_downsampler`` hands to ``AliasFreeDownsample2D``; the aliasing original itself has
-    no kernel in this build."""
+    ``replace_downsampler`` hands to ``AliasFreeDownsample2D``."""
 
     def __init__(self, channels: int, use_conv: bool = True, out_channels: Optional[int] = None,
                  padding: int = 1, name: str = "op"):
@@ -217,7 +226,13 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, self.out_channels, 3, stride=2, padding=padding)
 
     def forward(self, hidden_states, *args, **kwargs):
-        raise NotImplementedError("plain (aliasing) Downsample2D: call make_af_unet / make_af_vae first")
+        """The aliasing original (3x3 conv, stride 2): the stride-1 'same' convolution sampled on the stride-2 grid -
+        even positions for padding 1, odd positions for the padding-0 form that pads (0, 1, 0, 1) first (diffusers
+        Downsample2D).  Not on the alias-free path (surgery replaces it); kept so that a model can be
+        run before ``make_af_*`` for an A/B of the aliasing baseline."""
+        w, b, k = conv_params(self.conv)
+        h = ops.conv2d(ops.nhwc(hidden_states), w, b, k)
+        return _decimate2(ops.to_nchw_contiguous(h), 0 if self.padding == 1 else 1)
 
 
 class Upsample2D(nn.Module):
@@ -233,7 +248,15 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=1)
 
     def forward(self, hidden_states, output_size=None, *args, **kwargs):
-        raise NotImplementedError("plain (aliasing) Upsample2D: call make_af_unet / make_af_vae first")
+        """The aliasing original: nearest-neighbour x2 (``F.interpolate`` in diffusers) followed by the 3x3 conv."""
+        x = ops.to_nchw_contiguous(ops.nhwc(hidden_states))
+        n = x.shape[-1]
+        rep = np.repeat(np.eye(n), 2, axis=0)                 # [2n, n]: row o copies sample o // 2
+        up = sep_transform(x, np.repeat(np.eye(x.shape[-2]), 2, axis=0), rep)
+        if not self.use_conv:
+            return up
+        w, b, k = conv_params(self.conv)
+        return ops.nchw_view(ops.conv2d(ops.nhwc(up), w, b, k, gn_stats=True))
 
 
 # --------------------------------------------------------------------------------- UNet blocks

@@ -80,6 +80,15 @@ AFLDM_API int afldm_filtered_act_f16out(const float* x, void* y, int B, int H, i
                                         const float* scale, const float* shift, float* workspace,
                                         size_t workspace_floats, afldm_stream_t stream);
 
+/* The tcgen05 form of the filtered activation (csrc/fact_tc.cu), selected explicitly: every 1-D circular convolution of
+ * y = D act(U x U^T) D^T is a tcgen05.mma.kind::f16 GEMM with 128 lines as M (operands written by the threads into
+ * SWIZZLE_128B K-major / MN-major tiles, accumulators in TMEM, 3-term fp16 split = fp32 accuracy).  Planes 16 x 16
+ * (C % 16 == 0) and 32 x 32 (C % 8 == 0), 16-byte aligned x / y; AFLDM_E_NOKERNEL otherwise.  y_half != 0: y holds IEEE
+ * binary16.  The default dispatch of afldm_filtered_act_* selects this kernel only under AFLDM_FACT_TC=1: on B200 the
+ * warp-level mma.sync kernel is faster at these plane sizes (profiles/r02_fact_tc.md). */
+AFLDM_API int afldm_filtered_act_tc(const float* x, void* y, int y_half, int B, int H, int W, int C, int act,
+                                    const float* scale, const float* shift, afldm_stream_t stream);
+
 /* The same with the GroupNorm finalised inside the kernel from the partial sums the producer of x emitted
  * (afldm_conv2d_f32 gn_partial; channels [0,Ca) from partial_a, [Ca,Ca+Cb) from partial_b as in
  * afldm_groupnorm_finalize_f32): GroupNorm -> filtered activation costs ONE launch and one pass over x.

@@ -61,6 +61,20 @@ def main():
     ops["up8_y"] = R.UpsampleRFFT(8)(x8).numpy()
     ops["subpix_x"] = x8.numpy()
     ops["subpix_y"] = R.subpixel_shift(x8, up=2, shift_x=1, shift_y=1).contiguous().numpy()
+    # module surface beyond the two hot configurations (ideal_lpf.py:52-172): full-resolution LPF at several cutoffs,
+    # the reconstruction filter, other up factors, odd-friendly sizes, sub-pixel shifts
+    x12 = randn((1, 3, 12, 12), 31)
+    ops["surf_x12"] = x12.numpy()
+    ops["surf_lpf12_c50"] = R.LPF_RFFT(0.5)(x12.clone()).numpy()
+    ops["surf_lpf12_c25"] = R.LPF_RFFT(0.25)(x12.clone()).numpy()
+    ops["surf_recon12_c50"] = R.LPF_RECON_RFFT(0.5)(x12.clone()).numpy()
+    ops["surf_up3_12"] = R.UpsampleRFFT(3)(x12).numpy()
+    ops["surf_up2_12"] = R.UpsampleRFFT(2)(x12).numpy()
+    x16 = randn((2, 2, 16, 16), 32)
+    ops["surf_x16"] = x16.numpy()
+    ops["surf_lpf16_c50"] = R.LPF_RFFT(0.5)(x16.clone()).numpy()
+    ops["surf_up4_16"] = R.UpsampleRFFT(4)(x16).numpy()
+    ops["surf_subpix4_16"] = R.subpixel_shift(x16, up=4, shift_x=3, shift_y=-2).contiguous().numpy()
     np.savez_compressed(os.path.join(OUT, "ideal_ops.npz"), **ops)
 
     # ---- upfirdn2d (a16, BASELINE config #1)
@@ -94,6 +108,20 @@ def main():
         sh[f"shift{k}_t"] = np.array([ti, tj])
         sh[f"shift{k}_img"] = w.contiguous().numpy()
         sh[f"shift{k}_mask"] = m.numpy()
+    # the default (bilinear flow_warp) shifter on an image-sized tensor, 'ideal' (no crop) and the Fourier shifter
+    img = randn((2, 3, 24, 24), 78)
+    sh["img"] = img.numpy()
+    bil = RS.ImageShifter()
+    for k, (ti, tj) in enumerate([(0.0, 1.0), (0.0, 2.5), (1.75, -3.25), (-4.0, 0.5)]):
+        w, m = bil.shift(img, ti, tj)
+        sh[f"bil{k}_t"] = np.array([ti, tj])
+        sh[f"bil{k}_img"] = w.contiguous().numpy()
+        sh[f"bil{k}_mask"] = m.numpy()
+    w, m = RS.ImageShifter("ideal", 8).shift(lat, 0.5, -1.375)
+    sh["ideal_img"], sh["ideal_mask"] = w.contiguous().numpy(), m.numpy()
+    sh["fourier_img"] = RS.fourier_shift_batch(img, 0.75, -2.3, device="cpu").numpy()
+    w, m = RS.ImageShifter("fourier_crop").shift(img, 1.5, 0.25)
+    sh["fcrop_img"], sh["fcrop_mask"] = w.contiguous().numpy(), m.numpy()
     a, b = randn((2, 3, 16, 16), 3), randn((2, 3, 16, 16), 4)
     m = RS.gen_valid_mask(a.shape, 2.5, -1.25)
     sh["m_a"], sh["m_b"], sh["m_mask"] = a.numpy(), b.numpy(), m.numpy()

@@ -1,0 +1,140 @@
+"""GPU: the reference-named module surface (afldm.af_libs.ideal_lpf, afldm.shift_utils, afldm.af_libs...upfirdn2d) on the
+sm_100a kernels against the UNMODIFIED reference's golden outputs, the explicit tcgen05 filtered-activation entry point,
+and the base (aliasing) resamplers against the oracle."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "afldm", "_compat")):
+    if p not in sys.path:
+        sys.path.append(p)
+
+from afldm.af_libs import ideal_lpf as IL                          # noqa: E402  (the reference's module path)
+from afldm.af_libs.torch_utils.ops import upfirdn2d as U           # noqa: E402
+from afldm.shift_utils import flow_utils as FU                     # noqa: E402
+from afldm.shift_utils.metrics import mask_psnr                    # noqa: E402
+from afldm.shift_utils.shifters import ImageShifter, fourier_shift_batch   # noqa: E402
+from afldm_b200 import _lib, ops                                   # noqa: E402
+from oracle import ideal_lpf as OL                                 # noqa: E402
+from oracle import nn as ON                                        # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def test_ideal_lpf_module_surface_vs_reference_goldens(golden):
+    g = golden("ideal_ops")
+    x12, x16 = dev(g["surf_x12"]), dev(g["surf_x16"])
+    cases = [(IL.LPF_RFFT(0.5), x12, "surf_lpf12_c50"), (IL.LPF_RFFT(0.25), x12, "surf_lpf12_c25"),
+             (IL.LPF_RECON_RFFT(0.5), x12, "surf_recon12_c50"), (IL.UpsampleRFFT(3), x12, "surf_up3_12"),
+             (IL.UpsampleRFFT(2), x12, "surf_up2_12"), (IL.LPF_RFFT(), x16, "surf_lpf16_c50"),
+             (IL.UpsampleRFFT(4), x16, "surf_up4_16")]
+    for mod, x, key in cases:
+        got = mod(x).contiguous().cpu().numpy()
+        np.testing.assert_allclose(got, g[key], atol=1e-5, err_msg=key)
+    got = IL.subpixel_shift(x16, up=4, shift_x=3, shift_y=-2).cpu().numpy()
+    np.testing.assert_allclose(got, g["surf_subpix4_16"], atol=1e-5)
+    # the two hot configurations through the same classes (fused kernels)
+    for name in ("s8", "s32", "s64"):
+        x = dev(g[f"{name}_x"])
+        np.testing.assert_allclose(IL.UpsampleRFFT()(x).contiguous().cpu().numpy(), g[f"{name}_up2"], atol=1e-5)
+        full = IL.LPF_RFFT(0.5)(x)
+        np.testing.assert_allclose(full[:, :, ::2, ::2].contiguous().cpu().numpy(), g[f"{name}_lpf_down2"], atol=1e-5)
+    with pytest.raises(_lib.AfldmError):
+        IL.LPF_RFFT()(torch.zeros(1, 1, 8, 6, device=DEV))       # the reference's mask is square (ideal_lpf.py:81)
+
+
+def test_image_shifter_modes_vs_reference_goldens(golden):
+    g = golden("shift")
+    img, lat = dev(g["img"]), dev(g["lat"])
+    bil = ImageShifter()                                           # default = bilinear flow warp
+    for k in range(4):
+        ti, tj = (float(v) for v in g[f"bil{k}_t"])
+        w, m = bil.shift(img, ti, tj)
+        np.testing.assert_allclose(w.cpu().numpy(), g[f"bil{k}_img"], atol=1e-5)
+        assert m.shape == (2, 1, 24, 24) and np.array_equal(m.cpu().numpy(), g[f"bil{k}_mask"])
+    w, m = ImageShifter("ideal", 8).shift(lat, 0.5, -1.375)
+    np.testing.assert_allclose(w.cpu().numpy(), g["ideal_img"], atol=2e-5)
+    np.testing.assert_allclose(fourier_shift_batch(img, 0.75, -2.3, DEV).cpu().numpy(), g["fourier_img"], atol=2e-5)
+    w, m = ImageShifter("fourier_crop").shift(img, 1.5, 0.25)
+    np.testing.assert_allclose(w.cpu().numpy(), g["fcrop_img"], atol=2e-5)
+    assert np.array_equal(m.cpu().numpy(), g["fcrop_mask"])
+    # flow_warp with the uniform flow ImageShifter builds (shifters.py:200-205)
+    flow = torch.tensor([-1.75, 3.25]).view(1, 2, 1, 1).repeat(2, 1, 24, 24).to(DEV)
+    w2, m2 = FU.flow_warp(img, flow, True)
+    np.testing.assert_allclose(w2.cpu().numpy(), g["bil2_img"], atol=1e-5)
+    assert np.array_equal(m2.unsqueeze(1).float().cpu().numpy(), g["bil2_mask"])
+    # metric on device tensors = the reference's figure
+    a, b, mk = dev(g["m_a"]), dev(g["m_b"]), dev(g["m_mask"])
+    assert float(mask_psnr(a, b, mk)) == pytest.approx(float(g["mask_psnr"]), rel=1e-5)
+
+
+def test_upfirdn2d_python_surface_vs_reference_goldens(golden):
+    g = golden("upfirdn2d")
+    x = dev(g["x"])
+    f = U.setup_filter([1, 3, 3, 1], device=DEV)
+    np.testing.assert_allclose(f.cpu().numpy(), g["f1331"], atol=0)
+    np.testing.assert_allclose(U.upsample2d(x, f, up=2).cpu().numpy(), g["up2"], atol=2e-6)
+    np.testing.assert_allclose(U.downsample2d(x, f, down=2).cpu().numpy(), g["down2"], atol=2e-6)
+    np.testing.assert_allclose(U.filter2d(x, f).cpu().numpy(), g["filter2d"], atol=2e-6)
+    f12 = U.setup_filter([1, 2, 4, 7, 9, 11, 11, 9, 7, 4, 2, 1], device=DEV)
+    assert f12.ndim == 1
+    np.testing.assert_allclose(U.upsample2d(x, f12, up=2).cpu().numpy(), g["up2_f12"], atol=2e-6)
+    xs, fa = dev(g["xs"]), dev(g["fa"])
+    got = U.upfirdn2d(xs, fa, up=3, down=2, padding=[2, 1, 0, 3], flip_filter=True, gain=1.7)
+    np.testing.assert_allclose(got.cpu().numpy(), g["gen"], atol=2e-6)
+
+
+@pytest.mark.parametrize("b,c,n", [(2, 8, 32), (3, 192, 32), (16, 576, 32), (2, 16, 16), (5, 384, 16)])
+def test_filtered_act_tcgen05_entry_point(b, c, n):
+    """afldm_filtered_act_tc: the tcgen05 / TMEM form (csrc/fact_tc.cu) against the oracle's FFT form - the same bounds
+    as the mma.sync kernel (fp32 accuracy from the 3-term fp16 split), fp32 and fp16 stores, with and without affine."""
+    L = _lib.lib()
+    gen = torch.Generator().manual_seed(100 * n + c)
+    x = (torch.randn(b, c, n, n, generator=gen) * 1.5).to(DEV)
+    sc = (torch.rand(b, c, generator=gen) + 0.5).to(DEV).contiguous()
+    sh = (torch.randn(b, c, generator=gen) * 0.3).to(DEV).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    want = OL.filtered_act_fft(x * sc[:, :, None, None] + sh[:, :, None, None])
+    y = torch.empty_like(xn)
+    _lib.check(L.afldm_filtered_act_tc(xn.data_ptr(), y.data_ptr(), 0, b, n, n, c, 1, sc.data_ptr(), sh.data_ptr(), st))
+    assert (y.permute(0, 3, 1, 2) - want).abs().max().item() < 1e-5
+    yh = torch.empty(xn.shape, dtype=torch.float16, device=DEV)
+    _lib.check(L.afldm_filtered_act_tc(xn.data_ptr(), yh.data_ptr(), 1, b, n, n, c, 1, sc.data_ptr(), sh.data_ptr(), st))
+    assert torch.equal(yh, y.to(torch.float16))                    # the fp16 store is the rounding of the fp32 result
+    yi = torch.empty_like(xn)
+    _lib.check(L.afldm_filtered_act_tc(xn.data_ptr(), yi.data_ptr(), 0, b, n, n, c, 0, None, None, st))
+    assert (yi.permute(0, 3, 1, 2) - OL.filtered_act_fft(x, act=lambda t: t)).abs().max().item() < 1e-5
+    # and against the default kernel of the library on the same input
+    ref = ops.filtered_act(xn, sc, sh)
+    assert (ref - y).abs().max().item() < 1e-5
+    assert L.afldm_filtered_act_tc(xn.data_ptr(), y.data_ptr(), 0, b, 8, 8, c, 1, None, None, st) == -3   # outside the family
+
+
+def test_base_resamplers_match_oracle():
+    """The aliasing originals (diffusers Downsample2D / Upsample2D) that the surgery replaces."""
+    from afldm_b200.models import blocks as B
+    torch.manual_seed(3)
+    for pad in (1, 0):
+        ref = ON.Downsample2D(64, True, 64, padding=pad).to(DEV)
+        mine = B.Downsample2D(64, True, 64, padding=pad).to(DEV)
+        mine.load_state_dict(ref.state_dict())
+        x = torch.randn(2, 64, 16, 16, device=DEV)
+        with torch.no_grad():
+            torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=0, atol=5e-5)
+    ref = ON.Upsample2D(64, True, 64).to(DEV)
+    mine = B.Upsample2D(64, True, 64).to(DEV)
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 64, 8, 8, device=DEV)
+    with torch.no_grad():
+        torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=0, atol=5e-5)
