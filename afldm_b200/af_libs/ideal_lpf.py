@@ -93,8 +93,9 @@ def _square(x: torch.Tensor, who: str) -> int:
     return x.shape[-1]
 
 
-def _fused_ok(n: int) -> bool:
-    return n in (2, 4, 8, 16, 32, 64, 128)
+def _fused_ok(n: int, c: int) -> bool:
+    """The fused resampling kernels take power-of-two planes up to 128 and channel counts that are multiples of 32."""
+    return n in (2, 4, 8, 16, 32, 64, 128) and c % 32 == 0
 
 
 class LPF_RFFT(nn.Module):
@@ -137,7 +138,7 @@ class UpsampleRFFT(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n = _square(x, "UpsampleRFFT")
-        if self.up == 2 and self.factor == 1.0 and _fused_ok(n):
+        if self.up == 2 and self.factor == 1.0 and _fused_ok(n, x.shape[1]):
             return ops.nchw_view(ops.up2_ideal(ops.nhwc(x)))
         if self.up == 1 and self.factor == 1.0:
             return self.recon_filter(x)
@@ -150,7 +151,7 @@ class LPFDown2(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n2 = _square(x, "LPFDown2")
-        if n2 % 2 == 0 and _fused_ok(n2 // 2):
+        if n2 % 2 == 0 and _fused_ok(n2 // 2, x.shape[1]):
             return ops.nchw_view(ops.lpf_down2(ops.nhwc(x)))
         d = filter_matrix(n2, 0.5, 0.0)[::2, :]
         return sep_transform(x, d, d)

@@ -113,6 +113,14 @@ class AutoencoderKL(nn.Module):
                              down_filtered_act=list(down_filtered_act), up_filtered_act=list(up_filtered_act),
                              up_rescale=list(up_rescale), up_block_types=list(up_block_types),
                              down_block_types=list(down_block_types))
+        # keys of the diffusers config.json that do not change this build's graph are carried through unchanged, so a
+        # saved config reloads in diffusers with the same values (sample_size, norm_num_groups, act_fn, use_quant_conv...)
+        carried = dict(sample_size=512, norm_num_groups=32, act_fn="silu", use_quant_conv=True, use_post_quant_conv=True,
+                       force_upcast=True, latents_mean=None, latents_std=None, shift_factor=None, mid_block_add_attention=True)
+        for k, default in carried.items():
+            setattr(self.config, k, unused.get(k, default))
+        if self.config.norm_num_groups != 32 or self.config.act_fn != "silu":
+            raise NotImplementedError("AutoencoderKL: norm_num_groups = 32 and act_fn = 'silu' (the AF-LDM VAE)")
         self.up_block_types = list(up_block_types)        # read by scripts/shift_ldm_ffhq.py:60
         self.encoder = Encoder(in_channels, latent_channels, block_out_channels, layers_per_block)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block)

@@ -80,7 +80,7 @@ class ResnetBlock2D(nn.Module):
         if self.conv_shortcut is not None and ops.SHORTCUT_SIDE_STREAM and x.is_cuda and (skip is None or warped):
             main, side = torch.cuda.current_stream(x.device), ops.side_stream(x.device)
             side.wait_stream(main)
-            with torch.cuda.stream(side), ops.scratch_slot(ops.SIDE_SCRATCH_SLOT):
+            with torch.cuda.stream(side), ops.scratch_slot(ops.side_scratch_slot()):
                 ws, bs, ks = conv_params(self.conv_shortcut)
                 sc = ops.conv2d_cat(x, xs, ws, bs, ks) if skip is not None else ops.conv2d(x, ws, bs, ks)
         if skip is not None:

@@ -95,7 +95,10 @@ _scratch_retired = []   # outgrown buffers stay alive: captured CUDA graphs may 
 def scratch(device: torch.device, nfloats: int) -> torch.Tensor:
     """One grow-only fp32 scratch buffer per (device, slot) (split-K partials, large-plane intermediates).
     Ops on one stream run in order, so consecutive users may share it; code that runs concurrently on a second
-    stream (the second half-batch branch of a captured step) selects its own buffer with ``scratch_slot(1)``."""
+    stream (the second half-batch branch of a captured step, a resnet's conv_shortcut side stream) selects its own
+    buffer with ``scratch_slot(k)``.  RESTRICTION: work issued by the USER on two streams of one device at the same
+    time (say a UNet step on one stream and a VAE decode on another) must wrap one of them in ``scratch_slot(k)``,
+    k >= 4, as well - the library keeps no per-stream state ("Threading / streams")."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), _scratch_slot)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nfloats:
@@ -113,6 +116,12 @@ _side_streams = {}
 # input only and is needed by conv2's epilogue, so it runs under norm1 / activation / conv1 instead of between them
 SHORTCUT_SIDE_STREAM = os.environ.get("AFLDM_SC_SIDE", "1") == "1"
 SIDE_SCRATCH_SLOT = 2
+
+
+def side_scratch_slot() -> int:
+    """Scratch slot of the conv_shortcut side stream, derived from the caller's slot: two concurrently running
+    branches (``scratch_slot(0)`` / ``scratch_slot(1)``) get the distinct side buffers 2 / 3."""
+    return SIDE_SCRATCH_SLOT + _scratch_slot
 
 
 def side_stream(dev: torch.device) -> "torch.cuda.Stream":

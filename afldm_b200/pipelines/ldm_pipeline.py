@@ -37,14 +37,32 @@ def randn_tensor(shape, generator=None, device=None, dtype=torch.float32):
     return x.to(device) if device is not None else x
 
 
+def graph_signature(unet) -> tuple:
+    """Everything a captured step bakes in: the storage and version of every parameter (the packed weight copies of
+    ``packing`` are rebuilt from them, and the capture holds raw pointers to those copies), the attention processors,
+    the convolution algorithm and the feature switches.  ``MyLDMPipeline.graphed`` re-captures when it changes."""
+    params = tuple((p.data_ptr(), p._version) for p in unet.parameters())
+    procs = tuple(id(m.get_processor()) for m in unet.modules() if hasattr(m, "get_processor"))
+    return (params, procs, ops.default_conv_algo(), ops.F16_CONV, ops.F16_ATTENTION, ops.FUSE_GN_PROLOGUE,
+            ops.FUSE_CONCAT, ops.SHORTCUT_SIDE_STREAM)
+
+
+def graph_capturable(unet) -> bool:
+    """The captured step covers the default attention processors only: a ``CrossFrameAttnProcessor`` keys host-side
+    dictionaries by timestep and (in STORE state) would keep pointers into the graph's private memory pool."""
+    from ..models.blocks import AttnProcessor2_0
+    return all(type(m.get_processor()) is AttnProcessor2_0 for m in unet.modules() if hasattr(m, "get_processor"))
+
+
 class GraphedDenoiser:
     """One denoising step ``x <- cx * x + ce * unet(x, t)`` captured in a CUDA graph.
 
     ``x`` (NHWC, updated in place), ``t`` [B] and ``coef`` [2] are static device buffers."""
 
-    def __init__(self, unet: UNet2DModel, batch: int, warmup: int = 2):
+    def __init__(self, unet: UNet2DModel, batch: int, warmup: int = 2, size: Optional[int] = None):
         dev = unet.device
-        c, s = unet.config.in_channels, unet.config.sample_size
+        self.signature = graph_signature(unet)
+        c, s = unet.config.in_channels, (size or unet.config.sample_size)
         self.unet = unet
         self.x = torch.zeros((batch, s, s, c), dtype=torch.float32, device=dev)
         self.t = torch.ones((batch,), dtype=torch.float32, device=dev)
@@ -93,6 +111,8 @@ class MyLDMPipeline:
     def __init__(self, vae: AliasFreeAutoencoderKL, unet: UNet2DModel, scheduler: DDIMScheduler):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self._graphs = {}
+        self._tables = {}
+        self._graph_ok = None
         self._bar = {}
 
     # ------------------------------------------------------------------ construction
@@ -142,6 +162,7 @@ class MyLDMPipeline:
         if self.vae is not None:
             self.vae.to(device)
         self._graphs.clear()
+        self._tables = {}
         return self
 
     @property
@@ -158,10 +179,17 @@ class MyLDMPipeline:
         return tqdm(iterable, **{k: v for k, v in self._bar.items() if k != "disable"})
 
     # ------------------------------------------------------------------ denoising
-    def graphed(self, batch: int) -> GraphedDenoiser:
-        g = self._graphs.get(batch)
+    def graphed(self, batch: int, check: bool = True, size: Optional[int] = None) -> GraphedDenoiser:
+        """The captured step for this batch size; re-captured when anything it baked in has changed since
+        (``load_state_dict``, an in-place weight update, other attention processors, another conv algorithm).
+        The check walks the module tree (~2 ms of host time): ``denoise`` runs it at the start of a trajectory
+        (``start == 0``), not for every window of one."""
+        key = batch if size in (None, self.unet.config.sample_size) else (batch, size)
+        g = self._graphs.get(key)
+        if g is not None and check and g.signature != graph_signature(self.unet):
+            g = None
         if g is None:
-            g = self._graphs[batch] = GraphedDenoiser(self.unet, batch)
+            g = self._graphs[key] = GraphedDenoiser(self.unet, batch, size=size)
         return g
 
     def step_tables(self, num_inference_steps: int, batch: int):
@@ -173,19 +201,30 @@ class MyLDMPipeline:
         return tt.to(self.device), coefs.to(self.device)
 
     @torch.no_grad()
-    def denoise(self, latents: torch.Tensor, num_inference_steps: int = 50, use_cuda_graph: bool = True):
-        """DDIM loop of ldm_pipeline.py:103-109 (eta = 0) on device-resident latents [B,C,H,W]."""
-        latents = latents.to(device=self.device, dtype=torch.float32)
-        if not use_cuda_graph:
+    def denoise(self, latents: torch.Tensor, num_inference_steps: int = 50, use_cuda_graph: bool = True,
+                start: int = 0, stop: Optional[int] = None):
+        """DDIM loop of ldm_pipeline.py:103-109 (eta = 0) on latents [B,C,H,W] (device or - pinned - host memory; the
+        result stays on the device).  ``start`` / ``stop`` select a window [start, stop) of the schedule's steps, so a
+        trajectory can be advanced piecewise.  The captured-graph path needs the default attention processors; with
+        any other processor installed the loop runs eagerly."""
+        latents = latents.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        stop = num_inference_steps if stop is None else stop
+        if start == 0 or self._graph_ok is None:        # decided at the start of a trajectory, kept for its windows
+            self._graph_ok = graph_capturable(self.unet)
+        if not use_cuda_graph or not self._graph_ok:
             self.scheduler.set_timesteps(num_inference_steps)
-            for t in self.progress_bar(self.scheduler.timesteps):
+            for t in self.progress_bar(self.scheduler.timesteps[start:stop]):
                 eps = self.unet(self.scheduler.scale_model_input(latents, t), int(t)).sample
                 latents = self.scheduler.step(eps, int(t), latents).prev_sample
             return ops.to_nchw_contiguous(ops.nhwc(latents))
-        g = self.graphed(latents.shape[0])
-        tt, coefs = self.step_tables(num_inference_steps, latents.shape[0])
+        g = self.graphed(latents.shape[0], check=start == 0, size=latents.shape[-1])
+        key = (num_inference_steps, latents.shape[0])
+        if self._tables.get("key") != key:
+            self._tables = {"key": key, "tt": None}
+            self._tables["tt"], self._tables["coef"] = self.step_tables(num_inference_steps, latents.shape[0])
+        tt, coefs = self._tables["tt"], self._tables["coef"]
         g.x.copy_(ops.nhwc(latents))
-        for i in self.progress_bar(range(num_inference_steps)):
+        for i in self.progress_bar(range(start, stop)):
             g.t.copy_(tt[i])
             g.coef.copy_(coefs[i])
             g.replay()

@@ -7,13 +7,17 @@
         --master-port P bench.py --gpus N --steps K --warmup W           # N > 1: one rank per GPU
 
 Workload (config #2 of BASELINE.json): the FFHQ alias-free UNet (256.4 M parameters, random init
-under seed 0, `make_af_unet` applied), latents 16 x 4 x 32 x 32 per GPU (seed 0), DDIM eta = 0.
-One "step" = one UNet forward + DDIM update of the whole B = 16 batch.  N GPUs run N independent
-batches of 16 (weak scaling, no collective inside the step loop).
+under seed 0, `make_af_unet` applied), the seed-0 latents 16 x 4 x 32 x 32, DDIM eta = 0.
+One "step" = one UNet forward + DDIM update of the whole B = 16 batch.  N GPUs SHARD that batch
+(16 / N trajectories per rank, `afldm_b200.parallel.shard_batch`; strong scaling, no collective inside the
+step loop) and finish with ONE all-gather of the decoded frames (`parallel.gather_frames`).
 
-One JSON line on stdout (rank 0).  `value` = steps/s with latents resident in HBM (CUDA-graph
-replays timed with CUDA events); `e2e` = the same step through the public pipeline call with the
-latents coming from / returning to pinned host memory every step.
+One JSON line on stdout (rank 0).  `value` = steps/s of the global batch with the latents resident in
+HBM (CUDA-graph replays timed with CUDA events, max over ranks); `e2e` = the same steps through the
+public call `MyLDMPipeline.denoise(host_latents, ..., start=i, stop=i+1)` with the latents coming from /
+returning to pinned host memory every step, plus (reported beside it) the pipeline tail: alias-free VAE
+decode of the shard and the single all-gather.  Other workloads (`--workload vae_decode | i2sb | upfirdn2d`)
+print the same contract line for BASELINE configs #3 / #5 / #1.
 """
 from __future__ import annotations
 
@@ -32,7 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = "unet_denoising_steps_per_sec"
 UNIT = "steps/s"
 BATCH = 16
-WORKLOAD = "FFHQ AF-LDM UNet2DModel (256.4M params, make_af_unet), latents 16x4x32x32 per GPU, DDIM eta=0"
+WORKLOAD = "FFHQ AF-LDM UNet2DModel (256.4M params, make_af_unet), seed-0 latents 16x4x32x32 sharded over the GPUs, DDIM eta=0"
 
 
 def ncu_traffic(kind):
@@ -40,7 +44,7 @@ def ncu_traffic(kind):
     The convolution kernel is ONE template (conv_tc_kernel) whose tf32- and fp16-operand instantiations are listed as one
     family ("conv2d_tf32" in the capture summary): both bench names map to it."""
     key = "conv2d_tf32" if kind.startswith("conv2d") else kind
-    for name in ("r01_traffic_f16.json", "r01_traffic.json"):
+    for name in ("r02_traffic.json", "r01_traffic_f16.json", "r01_traffic.json"):
         try:
             return float(json.load(open(os.path.join(ROOT, "profiles", name)))[key]["dram_bytes_per_launch"])
         except Exception:
@@ -183,7 +187,7 @@ def run_reference(args):
         eager = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 / rate, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH, "where": "host CPU, PyTorch eager fp32"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -194,11 +198,23 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------- per-kernel timing
-def time_records(records, torch, reps=10):
-    """Device time of every distinct recorded C call: `reps` back-to-back launches are captured in a CUDA
-    graph and the replay is timed with CUDA events (no host launch gaps inside the timed region).
-    Returns {(name, key): [count, ms_per_launch, meta, name]}."""
+class L2Flusher:
+    """Overwrites a buffer larger than the 126 MB L2 between timed launches."""
+
+    def __init__(self, torch, dev, mbytes=256):
+        self.buf = torch.empty(mbytes << 18, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_records(records, torch, dev, reps=5):
+    """Device time of every distinct recorded C call, each launch timed ALONE with CUDA events after an L2 flush (cold
+    cache: weights and activations come from HBM, as the weights do inside the step; the activations of a real step are
+    L2-resident, so HBM-bound kernels read a little pessimistic here) - median of `reps`; the back-to-back, L2-hot figure
+    (10 launches in one graph, what round 1 reported) is kept beside it.  Returns {(name, key): [count, ms_cold, meta, ms_hot]}."""
     table = {}
+    flush = L2Flusher(torch, dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for name, meta, fn, _keep in records:
         key = (name, tuple(sorted((k, v) for k, v in meta.items())))
@@ -208,35 +224,136 @@ def time_records(records, torch, reps=10):
             continue
         fn()
         torch.cuda.synchronize()
+        cold = []
+        for _ in range(reps):
+            flush()
+            ev0.record()
+            fn()
+            ev1.record()
+            ev1.synchronize()
+            cold.append(ev0.elapsed_time(ev1))
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(reps):
+            for _ in range(10):
                 fn()
         g.replay()
         ev0.record()
         g.replay()
         ev1.record()
         ev1.synchronize()
-        table[key] = [1, ev0.elapsed_time(ev1) / reps, meta, name]
+        table[key] = [1, statistics.median(cold), meta, ev0.elapsed_time(ev1) / 10]
         del g
     return table
 
 
-def time_vae_decode(torch, dev, batch):
+def aggregate(table):
+    agg = {}
+    for (name, _key), (count, ms_cold, meta, ms_hot) in table.items():
+        a = agg.setdefault(name, dict(launches=0, ms=0.0, ms_hot=0.0, flops=0.0, bytes=0.0))
+        a["launches"] += count
+        a["ms"] += count * ms_cold
+        a["ms_hot"] += count * ms_hot
+        a["flops"] += count * meta.get("flops", 0.0)
+        if name == "filtered_act":
+            a["bytes"] += count * 8.0 * meta["elems"]
+        elif name == "up2_ideal":
+            a["bytes"] += count * 20.0 * meta["elems"]
+        elif name == "lpf_down2":
+            a["bytes"] += count * 5.0 * meta["elems"]
+    return agg
+
+
+def rooflines(agg, pk):
+    """Roofline of the dominant kernel family (by cold device time) and of the filtered activation (the kernel the north
+    star names).  Kernels are timed alone -> burst peaks (MEASURED_PEAKS.json), per the bench contract."""
+    top_name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    if a["flops"] > 0:
+        ach = a["flops"] / (a["ms"] / 1e3) / 1e12
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16"], "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"],
+                "avg_launch_ms": a["ms"] / a["launches"], "achieved_l2_hot": a["flops"] / (a["ms_hot"] / 1e3) / 1e12,
+                "peak_source": pk["source"] + ": bf16 burst figure (each launch is timed alone, after an L2 flush); "
+                               + ("operands are fp16 (tcgen05.mma.kind::f16), the same tensor rate as bf16"
+                                  if top_name == "conv2d_f16" else "operands are TF32, whose tensor peak is half the bf16 peak"),
+                "algorithmic_flops_per_step": a["flops"],
+                "traffic_unit": "DRAM bytes per launch, average over the conv_tc_kernel family of one step (ncu, profiles/)"}
+    else:
+        ach = a["bytes"] / (a["ms"] / 1e3) / 1e9
+        roof = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"], "avg_launch_ms": a["ms"] / a["launches"],
+                "peak_source": pk["source"] + " (copy bandwidth; each launch timed alone, after an L2 flush)"}
+    fir = None
+    fa = agg.get("filtered_act")
+    if fa:
+        ach = fa["bytes"] / (fa["ms"] / 1e3) / 1e9
+        fir = {"kernel": "filtered_act", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+               "achieved_l2_hot": fa["bytes"] / (fa["ms_hot"] / 1e3) / 1e9, "launches_per_step": fa["launches"],
+               "ms_per_step": fa["ms"], "ms_per_step_l2_hot": fa["ms_hot"],
+               "algorithmic_bytes_per_step": fa["bytes"], "traffic": ncu_traffic("filtered_act"),
+               "floors": "HBM by bytes; the formulation's own floors on B200 are 2 MUFU per SiLU on the 4x plane and "
+                         "(tcgen05 form) 57 B/clk/SM of TMEM reads - DESIGN.md section 3"}
+    return roof, fir
+
+
+def dump_breakdown(path, table):
+    with open(path, "w") as f:
+        f.write("kernel,count,us_each_cold,us_each_l2_hot,us_total_cold,tflops_or_gbs_cold,meta\n")
+        for (name, _key), (count, ms_cold, meta, ms_hot) in sorted(table.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            rate = meta.get("flops", 0.0) / (ms_cold / 1e3) / 1e12 if meta.get("flops") else \
+                8.0 * meta.get("elems", 0) / (ms_cold / 1e3) / 1e9
+            f.write(f"{name},{count},{ms_cold * 1e3:.1f},{ms_hot * 1e3:.1f},{count * ms_cold * 1e3:.1f},{rate:.1f},"
+                    f"\"{json.dumps(meta)}\"\n")
+
+
+def parity_error(torch, dev, pipe, latents):
+    """The checker, after the timed regions: eps of ONE step of the benchmarked class at the benchmarked configuration
+    (B = 16, seed-0 latents, identical weights) against the fp32 oracle in PyTorch on the same GPU (TF32 off)."""
+    from oracle import af_blocks as OA
+    from oracle import nn as ON
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = ON.UNet2DModel().to(dev).eval()
+        ref.load_state_dict(pipe.unet.state_dict())
+        OA.make_af_unet(ref)
+        x = latents.to(dev)
+        with torch.no_grad():
+            want = ref(x, torch.tensor(981, device=dev)).sample
+            got = pipe.unet(x, 981).sample
+        d = (got - want).abs()
+        out = {"what": "eps of one UNet evaluation, B=16 seed-0 latents, t=981, vs the fp32 PyTorch oracle (TF32 off) with the same weights",
+               "max_abs": d.max().item(), "mean_abs": d.mean().item(), "eps_rms": want.pow(2).mean().sqrt().item(),
+               "rel_rms": (d.pow(2).mean().sqrt() / want.pow(2).mean().sqrt()).item(),
+               "tolerance_asserted_in_tests": "max 6e-3, mean 8e-4, rel-rms 2e-3 (tests/test_gpu_parity_headline.py)"}
+        del ref
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+def time_vae_decode(torch, dev, batch, pk, contract=False):
     """Alias-free VAE decode 32x32x4 -> 256x256x3 (BASELINE config #3: model_afvae.json architecture, random init
-    seed 0, z = randn(batch, 4, 32, 32) seed 0, decode(z / 0.6)); device-resident, CUDA events, eager warm-up, then 3 timed replays of the captured decode."""
+    seed 0, z = randn(batch, 4, 32, 32) seed 0, decode(z / 0.6)); device-resident, CUDA events, eager warm-up, then 3
+    timed replays of the captured decode.  `contract`: also the per-kernel roofline, the end-to-end figure (pinned host
+    latents in, pinned host images out) and the parity of the class against the oracle at B = 2."""
+    from afldm_b200 import ops
     from afldm_b200.models import AliasFreeAutoencoderKL
     torch.manual_seed(0)
     vae = AliasFreeAutoencoderKL.from_config().to(dev).eval()
     g = torch.Generator().manual_seed(0)
-    z = (torch.randn(batch, 4, 32, 32, generator=g) / 0.6).to(dev)
+    z_host = (torch.randn(batch, 4, 32, 32, generator=g) / 0.6)
+    z = z_host.to(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mode = "cuda_graph"
+    records = []
     with torch.no_grad():
+        if contract:
+            ops.record_to(records)
         out = vae.decode(z).sample                      # eager warm-up (also sizes the scratch buffers)
+        ops.record_to(None)
         torch.cuda.synchronize()
-        # The decode is ~180 launches; issued eagerly its wall time swings with host-side launch cost (measured 28 - 76 ms
-        # for the same 26 ms of kernels at B = 16), so it is replayed as a CUDA graph like the UNet step.
+        n0 = _launches()
         g = None
         try:
             g = torch.cuda.CUDAGraph()
@@ -247,6 +364,7 @@ def time_vae_decode(torch, dev, batch):
         except Exception:
             g, mode = None, "eager"
             torch.cuda.synchronize()
+        launches = _launches() - n0
         ev0.record()
         for _ in range(3):
             if g is not None:
@@ -255,12 +373,199 @@ def time_vae_decode(torch, dev, batch):
                 out = vae.decode(z).sample
         ev1.record()
         ev1.synchronize()
-    ms = ev0.elapsed_time(ev1) / 3
-    ok = bool(torch.isfinite(out).all().item()) and tuple(out.shape) == (batch, 3, 256, 256)
+        ms = ev0.elapsed_time(ev1) / 3
+        ok = bool(torch.isfinite(out).all().item()) and tuple(out.shape) == (batch, 3, 256, 256)
+        res = {"workload": f"AF-VAE decode {batch}x4x32x32 -> {batch}x3x256x256 (config #3), TF32 class, {mode} launches",
+               "images_per_s": batch / (ms / 1e3), "ms_per_decode": ms, "batch": batch, "finite_and_shaped": ok,
+               "launches_per_decode": launches}
+        if contract:
+            h_in = z_host.pin_memory()
+            h_out = torch.empty((batch, 3, 256, 256), dtype=torch.float32).pin_memory()
+            e2e = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                ev0.record()
+                img = vae.decode(h_in.to(dev, non_blocking=True)).sample
+                h_out.copy_(img, non_blocking=True)
+                ev1.record()
+                ev1.synchronize()
+                e2e.append(ev0.elapsed_time(ev1))
+            res["e2e_ms"] = statistics.median(e2e)
+            res["h2d_bytes"], res["d2h_bytes"] = h_in.numel() * 4, h_out.numel() * 4
+            table = time_records(records, torch, dev, reps=3)
+            agg = aggregate(table)
+            res["roofline"], res["roofline_filtered_act"] = rooflines(agg, pk)
+            tot = sum(a["ms"] for a in agg.values())
+            res["breakdown"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4)}
+                                for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
     del vae, out, g
     torch.cuda.empty_cache()
-    return {"workload": f"AF-VAE decode {batch}x4x32x32 -> {batch}x3x256x256 (config #3), TF32 class, {mode} launches",
-            "images_per_s": batch / (ms / 1e3), "ms_per_decode": ms, "batch": batch, "finite_and_shaped": ok}
+    return res
+
+
+def _launches():
+    from afldm_b200 import _lib
+    return _lib.launch_count()
+
+
+# --------------------------------------------------------------------------------------- side workloads (cfg #1 / #3 / #5)
+def run_vae_workload(args, torch, dev):
+    """BASELINE config #3 as a contract line: alias-free VAE decode, B = 64 on one B200."""
+    from oracle import af_blocks as OA
+    from oracle import nn as ON
+    pk = peaks()
+    with ClockSampler(dev.index or 0) as clk:
+        res = time_vae_decode(torch, dev, args.vae_batch, pk, contract=True)
+    # CPU baseline: the oracle decoder (reference ideal_lpf ops restated + diffusers blocks restated) on the host cores, 1 image
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    rv = ON.AutoencoderKL().eval()
+    OA.make_af_vae_from_config(rv)
+    z1 = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0)) / 0.6
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        rv.decode(z1)
+        cpu_s = time.perf_counter() - t0
+    line = {"metric": "afvae_decode_images_per_sec", "value": res["images_per_s"], "unit": "images/s", "n_gpus": 1,
+            "steps": 3, "warmup": 1, "ms_per_step": res["ms_per_decode"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 activations / accumulation; tensor-core products on 11-bit-significand operands (fp16 operand storage)",
+            "data": "synthetic",
+            "config": {"workload": res["workload"], "global_batch": args.vae_batch, "l2": "activations of one decode (> 10 GB at B = 64) >> 126 MB L2"},
+            "clocks": clk.summary(), "finite": res["finite_and_shaped"],
+            "e2e": {"value": args.vae_batch / (res["e2e_ms"] / 1e3), "unit": "images/s", "h2d_bytes_per_step": res["h2d_bytes"],
+                    "d2h_bytes_per_step": res["d2h_bytes"]},
+            "gpu_launches": res["launches_per_decode"] * 3, "roofline": res["roofline"],
+            "roofline_filtered_act": res["roofline_filtered_act"], "breakdown": res["breakdown"],
+            "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "1 image decoded by the oracle AF-VAE on the host cores (PyTorch eager fp32)"}}
+    print(json.dumps(line), flush=True)
+
+
+def run_i2sb_workload(args, torch, dev):
+    """BASELINE config #5, one GPU's share: the FFHQ UNet architecture at 64 x 64 latents, B = 16, I2SB bridge (ODE form,
+    i2sb_pipeline.py:45-56), captured step.  99 UNet evaluations per 100-step run; `steps` of them are timed."""
+    from afldm_b200 import ops
+    from afldm_b200.pipelines import I2SBLDMPipeline
+    from afldm_b200.schedulers import I2SBScheduler
+    from afldm_b200.models import UNet2DModel
+    from afldm_b200.af_modules.af_api import make_af_unet
+    ops.set_default_conv_algo(args.conv_algo)
+    torch.manual_seed(0)
+    unet = UNet2DModel.from_config()
+    make_af_unet(unet)
+    pipe = I2SBLDMPipeline(None, unet, I2SBScheduler.from_config()).to(dev)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(BATCH, 4, 64, 64, generator=g)
+    records = []
+    ops.record_to(records)
+    with torch.no_grad():
+        pipe.unet(lat.to(dev), 981)
+    ops.record_to(None)
+    gd = pipe.graphed(BATCH, size=64)
+    pipe.scheduler.set_timesteps(100)
+    ts = [int(t) for t in pipe.scheduler.timesteps][:99]
+    table = torch.tensor([[1.0, float(pipe.scheduler.coefficients(t)[0])] for t in ts], dtype=torch.float32, device=dev)
+    tt = torch.tensor(ts, dtype=torch.float32, device=dev)[:, None].expand(-1, BATCH).contiguous()
+    gd.x.copy_(ops.nhwc(lat.to(dev)))
+
+    def run(n, first):
+        for i in range(first, first + n):
+            gd.t.copy_(tt[i % 99])
+            gd.coef.copy_(table[i % 99])
+            gd.replay()
+
+    run(args.warmup, 0)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index or 0) as clk:
+        ev0.record()
+        run(args.steps, args.warmup)
+        ev1.record()
+        ev1.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    h_in = lat.pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    ev0.record()
+    for i in range(args.steps):
+        gd.x.copy_(ops.nhwc(h_in.to(dev, non_blocking=True)))
+        gd.t.copy_(tt[i % 99])
+        gd.coef.copy_(table[i % 99])
+        gd.replay()
+        h_out.copy_(ops.to_nchw_contiguous(gd.x), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ev1.record()
+    ev1.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    pk = peaks()
+    agg = aggregate(time_records(records, torch, dev, reps=3))
+    roof, fir = rooflines(agg, pk)
+    tot = sum(a["ms"] for a in agg.values())
+    line = {"metric": "i2sb_unet_steps_per_sec", "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "TF32 class (see the headline line)", "data": "synthetic",
+            "config": {"workload": "AF-I2SB SR UNet (FFHQ UNet architecture, 256.4M params) at 64x64x4 latents, B=16 per GPU "
+                                   "(config #5: B=128 over 8 GPUs), I2SB ODE update, CUDA-graph step", "global_batch": BATCH,
+                       "l2": "1.03 GB of weights per step >> 126 MB L2"},
+            "clocks": clk.summary(), "finite": bool(torch.isfinite(gd.x).all().item()),
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h_in.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4},
+            "gpu_launches": gd.launches_per_step * args.steps, "launches_per_step": gd.launches_per_step,
+            "roofline": roof, "roofline_filtered_act": fir,
+            "breakdown": {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4)}
+                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
+def run_upfirdn2d_workload(args, torch, dev):
+    """BASELINE config #1 (plumbing): upsample2d(x, [1,3,3,1], up=2) on 1x3x64x64, sm_100a kernel vs the CPU port."""
+    from afldm_b200.af_libs import upfirdn2d as U
+    from oracle import upfirdn2d as OU
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 3, 64, 64, generator=g)
+    f = U.setup_filter([1, 3, 3, 1])
+    xd, fd = x.to(dev), f.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        y = U.upsample2d(xd, fd, up=2)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(args.steps, 20)
+    n0 = _launches()
+    ev0.record()
+    for _ in range(n):
+        y = U.upsample2d(xd, fd, up=2)
+    ev1.record()
+    ev1.synchronize()
+    ms = ev0.elapsed_time(ev1) / n
+    h_in, h_out = x.pin_memory(), torch.empty(1, 3, 128, 128).pin_memory()
+    ev0.record()
+    for _ in range(n):
+        y = U.upsample2d(h_in.to(dev, non_blocking=True), fd, up=2)
+        h_out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ev1.record()
+    ev1.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1) / n
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        want = OU.upsample2d(x.numpy(), f.numpy(), up=2)
+    cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    err = float(abs(h_out.numpy() - want).max())
+    bytes_alg = 49152 + 196608
+    line = {"metric": "upfirdn2d_up2_calls_per_sec", "value": 1000.0 / ms, "unit": "calls/s", "n_gpus": 1, "steps": n, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "upfirdn2d.upsample2d(x, setup_filter([1,3,3,1]), up=2), x = 1x3x64x64 (config #1, plumbing)",
+                       "l2": "246 KB per call: cache-resident and launch-latency bound by construction"},
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "calls/s", "h2d_bytes_per_step": 49152, "d2h_bytes_per_step": 196608},
+            "gpu_launches": _launches() - n0,
+            "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms / 1e3) / 1e9, "peak": peaks()["hbm"], "unit": "GB/s",
+                         "frac": bytes_alg / (ms / 1e3) / 1e9 / peaks()["hbm"], "traffic": None,
+                         "note": "a 246 KB problem cannot load a B200: the time is one kernel launch"},
+            "cpu_baseline": {"value": 1000.0 / cpu_ms, "unit": "calls/s", "cores": 1, "kind": "port",
+                             "sample": f"{reps} calls of the numpy gather restatement (oracle/upfirdn2d.py)"},
+            "max_abs_err_vs_oracle": err}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -269,9 +574,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d"])
     ap.add_argument("--conv-algo", default=os.environ.get("AFLDM_CONV_ALGO", "tf32"), choices=["simt", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the eps-vs-oracle check of the benchmarked class")
     ap.add_argument("--dump-breakdown", default=None, help="write the per-shape kernel timing table (CSV) here")
     ap.add_argument("--no-vae", action="store_true", help="skip the alias-free VAE decode side measurement (config #3)")
     ap.add_argument("--vae-batch", type=int, default=64)
@@ -283,7 +590,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from afldm_b200 import _lib, ops
+    from afldm_b200 import _lib, ops, parallel
     from afldm_b200.pipelines import MyLDMPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,6 +600,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: afldm_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.workload != "unet":
+        if rank != 0:
+            return
+        ops.set_default_conv_algo(args.conv_algo)
+        return {"vae_decode": run_vae_workload, "i2sb": run_i2sb_workload, "upfirdn2d": run_upfirdn2d_workload}[args.workload](args, torch, dev)
     if world > 1:
         # NCCL prints its version banner to stdout when the communicator is created: route fd 1 to stderr around the
         # (eager, device_id=) initialisation and the first collective so that stdout carries ONE JSON line only
@@ -310,147 +622,164 @@ def main():
             os.close(saved_fd)
 
     ops.set_default_conv_algo(args.conv_algo)
-    pipe = MyLDMPipeline.from_config(seed=0, with_vae=False).to(dev)
-    g = torch.Generator().manual_seed(rank)                     # rank r denoises its own batch of 16
-    latents = torch.randn(BATCH, 4, 32, 32, generator=g)
+    pipe = MyLDMPipeline.from_config(seed=0, with_vae=True).to(dev)
+    g = torch.Generator().manual_seed(0)
+    latents = torch.randn(BATCH, 4, 32, 32, generator=g)          # the SAME seed-0 batch on every rank ...
+    shard = parallel.shard_batch(latents, rank, world).contiguous()      # ... of which this rank denoises its slice
+    bs = shard.shape[0]
+    if bs == 0:
+        raise SystemExit(f"--gpus {world}: more ranks than the {BATCH} trajectories of the workload")
     steps_total = args.steps + args.warmup
-    tt, coefs = pipe.step_tables(50, BATCH)
+    tt, coefs = pipe.step_tables(50, bs)
 
-    # ---- eager pass with the recorder on: the kernel list of one step (also the pre-capture warm-up)
+    # ---- eager pass with the recorder on: the kernel list of one step at this rank's batch (also the pre-capture warm-up)
     records = []
     ops.record_to(records)
     with torch.no_grad():
-        x = latents.to(dev)
+        x = shard.to(dev)
         eps = pipe.unet(x, tt[0]).sample
         ops.axpby(ops.nhwc(x), ops.nhwc(eps), coefs[0], None)
     ops.record_to(None)
     torch.cuda.synchronize()
 
-    gd = pipe.graphed(BATCH)
-    gd.x.copy_(ops.nhwc(latents.to(dev)))
+    gd = pipe.graphed(bs)
+    gd.x.copy_(ops.nhwc(shard.to(dev)))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(n, first):
-        for i in range(first, first + n):
-            gd.t.copy_(tt[i % 50])
-            gd.coef.copy_(coefs[i % 50])
-            gd.replay()
+    def allmax(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- device-resident timing
-    run(args.warmup, 0)
-    barrier()
+    def run(den, n, first):
+        for i in range(first, first + n):
+            den.t.copy_(tt_of[den][i % 50])
+            den.coef.copy_(coefs[i % 50])
+            den.replay()
+
+    tt_of = {gd: tt}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- device-resident timing (strong scaling: the global batch of 16 advances `steps` steps)
+    run(gd, args.warmup, 0)
+    barrier()
     with ClockSampler(local) as clk:
         ev0.record()
-        run(args.steps, args.warmup)
+        run(gd, args.steps, args.warmup)
         ev1.record()
         barrier()
-    ms = ev0.elapsed_time(ev1)
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    value = world * args.steps / (ms_max / 1000.0)
+    ms_max = allmax(ev0.elapsed_time(ev1))
+    value = args.steps / (ms_max / 1000.0)
     finite = bool(torch.isfinite(gd.x).all().item())
 
-    # ---- end to end: pinned host latents in, pinned host latents out, every step
-    h_in = torch.empty((BATCH, 32, 32, 4), dtype=torch.float32).pin_memory()
+    # ---- end to end through the public call: pinned host latents in, pinned host latents out, every step
+    h_in = shard.clone().pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
-    h_in.copy_(latents.permute(0, 2, 3, 1))
 
     def e2e_step(i):
-        gd.x.copy_(h_in, non_blocking=True)
-        gd.t.copy_(tt[i % 50])
-        gd.coef.copy_(coefs[i % 50])
-        gd.replay()
-        h_out.copy_(gd.x, non_blocking=True)
+        out = pipe.denoise(h_in, 50, start=i % 50, stop=i % 50 + 1)     # H2D of this step's input inside
+        h_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         h_in.copy_(h_out)                                       # the caller feeds the result back
 
-    for i in range(args.warmup):
+    for i in range(1, 1 + args.warmup):                          # windows with start > 0: the graph check is per trajectory
         e2e_step(i)
     barrier()
     ev0.record()
-    for i in range(args.warmup, steps_total):
+    for i in range(1 + args.warmup, 1 + steps_total):
         e2e_step(i)
     ev1.record()
     barrier()
-    e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    e2e_value = args.steps / (allmax(ev0.elapsed_time(ev1)) / 1000.0)
+
+    # ---- the pipeline tail: alias-free VAE decode of this rank's trajectories + the ONE collective of the path
+    def tail(lat_dev):
+        frames = pipe.decode_latents(lat_dev)
+        return parallel.gather_frames(frames, BATCH)
+
+    with torch.no_grad():
+        final_local = ops.to_nchw_contiguous(gd.x)
+        tail(final_local)                                        # warm-up (sizes scratch buffers, NCCL channel setup)
+        barrier()
+        ev0.record()
+        gathered = tail(final_local)
+        h_frames = gathered.to("cpu", non_blocking=False) if rank == 0 else None
+        ev1.record()
+        barrier()
+    tail_ms = allmax(ev0.elapsed_time(ev1))
+
+    # ---- the sharded result is the single-GPU result: rank 0 recomputes every rank's shard with the same kernels
+    # (same shapes -> bitwise) and also reports the distance to the monolithic B = 16 run (other tile / split-K plans)
+    verify = None
+    if rank == 0:
+        with torch.no_grad():
+            def trajectory(lat_host, den):
+                # what every rank did to its shard in the end-to-end region: the windows i = 1 .. warmup + steps
+                den.x.copy_(ops.nhwc(lat_host.to(dev)))
+                for i in range(1, 1 + steps_total):
+                    den.t.copy_(tt_of[den][i % 50])
+                    den.coef.copy_(coefs[i % 50])
+                    den.replay()
+                return pipe.decode_latents(ops.to_nchw_contiguous(den.x))
+            parts = [trajectory(parallel.shard_batch(latents, r, world).contiguous(), gd) for r in range(world)]
+            again = torch.cat(parts, dim=0)
+            bitwise = bool(torch.equal(again, gathered))
+            verify = {"gathered_equals_single_gpu_recompute_bitwise": bitwise, "frames": list(gathered.shape)}
+            if world > 1:
+                g16 = pipe.graphed(BATCH)
+                tt_of[g16] = pipe.step_tables(50, BATCH)[0]
+                mono = trajectory(latents, g16)
+                verify["max_abs_diff_vs_monolithic_b16"] = (mono - gathered).abs().max().item()
+                verify["frames_max_abs"] = mono.abs().max().item()
+        if not verify["gathered_equals_single_gpu_recompute_bitwise"]:
+            print("WARNING: gathered frames differ from the single-GPU recompute", file=sys.stderr)
+
+    # ---- weak scaling (labelled second field): every rank its own full batch of 16
+    weak = None
     if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / (float(e2e_ms.item()) / 1000.0)
+        g16 = pipe.graphed(BATCH)
+        tt_of[g16] = pipe.step_tables(50, BATCH)[0]
+        g16.x.copy_(ops.nhwc(torch.randn(BATCH, 4, 32, 32, generator=torch.Generator().manual_seed(rank)).to(dev)))
+        run(g16, args.warmup, 0)
+        barrier()
+        ev0.record()
+        run(g16, args.steps, args.warmup)
+        ev1.record()
+        barrier()
+        wms = allmax(ev0.elapsed_time(ev1))
+        weak = {"what": f"weak scaling: every rank denoises its OWN batch of 16 (global batch {BATCH * world})",
+                "value": world * args.steps / (wms / 1000.0), "unit": "batch-16 steps/s summed over ranks", "ms_per_step": wms / args.steps}
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0)
     pk = peaks()
     roofline, breakdown, fir = None, None, None
     if rank == 0 and not args.no_breakdown:
-        table = time_records(records, torch)
-        agg = {}
-        for (name, _key), (count, ms_each, meta, _n) in table.items():
-            a = agg.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
-            a["launches"] += count
-            a["ms"] += count * ms_each
-            a["flops"] += count * meta.get("flops", 0.0)
-            if name == "filtered_act":
-                a["bytes"] += count * 8.0 * meta["elems"]
-                # tensor work of the separable-GEMM form on mma.m16n8k16 (3-term fp16 split): 36 n FLOP per element
-                # for the planes that run on the tensor-core kernels (n = 16, 32), DESIGN.md section 6
-                if meta.get("N") in (16, 32):
-                    a["mma_flops"] = a.get("mma_flops", 0.0) + count * 36.0 * meta["N"] * meta["elems"]
-            elif name == "up2_ideal":
-                a["bytes"] += count * 20.0 * meta["elems"]
-            elif name == "lpf_down2":
-                a["bytes"] += count * 5.0 * meta["elems"]
+        table = time_records(records, torch, dev)
+        agg = aggregate(table)
         if args.dump_breakdown:
-            with open(args.dump_breakdown, "w") as f:
-                f.write("kernel,count,us_each,us_total,tflops_or_gbs,meta\n")
-                for (name, _key), (count, ms_each, meta, _n) in sorted(table.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
-                    rate = meta.get("flops", 0.0) / (ms_each / 1e3) / 1e12 if meta.get("flops") else \
-                        8.0 * meta.get("elems", 0) / (ms_each / 1e3) / 1e9
-                    f.write(f"{name},{count},{ms_each * 1e3:.1f},{count * ms_each * 1e3:.1f},{rate:.1f},"
-                            f"\"{json.dumps(meta)}\"\n")
+            dump_breakdown(args.dump_breakdown, table)
         total_iso = sum(a["ms"] for a in agg.values())
-        breakdown = {k: {"launches": v["launches"], "ms_per_step": round(v["ms"], 4),
+        breakdown = {k: {"launches": v["launches"], "ms_per_step": round(v["ms"], 4), "ms_per_step_l2_hot": round(v["ms_hot"], 4),
                          "share": round(v["ms"] / total_iso, 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-        top = max(agg.items(), key=lambda kv: kv[1]["ms"])
-        name, a = top
-        if a["flops"] > 0:
-            ach = a["flops"] / (a["ms"] / 1e3) / 1e12
-            roofline = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(name), "launches_per_step": a["launches"],
-                        "avg_launch_ms": a["ms"] / a["launches"],
-                        "peak_source": pk["source"] + " bf16 sustained (kernel timed inside the step's launch mix); "
-                                       + ("operands are fp16 (tcgen05.mma.kind::f16), the same tensor rate as bf16"
-                                          if name == "conv2d_f16" else
-                                          "operands are TF32, whose tensor peak is half the bf16 peak"),
-                        "algorithmic_flops_per_step": a["flops"], "traffic_unit": "DRAM bytes per launch, average over the conv_tc_kernel family of one step (ncu, profiles/r01_traffic_f16.json)"}
-        else:
-            ach = a["bytes"] / (a["ms"] / 1e3) / 1e9
-            roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": ncu_traffic(name), "launches_per_step": a["launches"],
-                        "avg_launch_ms": a["ms"] / a["launches"], "peak_source": pk["source"]}
-        fa = agg.get("filtered_act")
-        if fa:
-            ach = fa["bytes"] / (fa["ms"] / 1e3) / 1e9
-            fir = {"kernel": "filtered_act", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                   "frac": ach / pk["hbm"], "launches_per_step": fa["launches"], "ms_per_step": fa["ms"]}
-            if fa.get("mma_flops"):
-                # second ceiling of the formulation actually run: the warp-level tensor path (measured mma.sync fp16 rate,
-                # profiles/r01_mma_sync_rates.txt) - at n = 32 it, not HBM, is the nearer floor
-                tf = fa["mma_flops"] / (fa["ms"] / 1e3) / 1e12
-                fir["tensor_ceiling"] = {"flops_per_step": fa["mma_flops"], "achieved": tf, "peak": 553.6, "unit": "TFLOP/s",
-                                         "frac": tf / 553.6,
-                                         "peak_source": "measured mma.sync.m16n8k16 f16 rate on B200 (profiles/r01_mma_sync_rates.txt)"}
+        roofline, fir = rooflines(agg, pk)
+
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        try:
+            parity = parity_error(torch, dev, pipe, latents)
+        except Exception as e:
+            parity = {"error": str(e)[:200]}
 
     # ---- BASELINE config #3 (reported beside the headline, not part of it): alias-free VAE decode
     vae_decode = None
     if rank == 0 and world == 1 and not args.no_vae:
         try:
-            vae_decode = time_vae_decode(torch, dev, args.vae_batch)
+            vae_decode = time_vae_decode(torch, dev, args.vae_batch, pk)
         except Exception as e:                      # never lose the headline line over the side measurement
             vae_decode = {"error": str(e)[:200]}
 
@@ -462,22 +791,26 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": ("f32 residual stream / norms / softmax / accumulation; tensor-core products on 11-bit-significand "
                       "operands (resnet 3x3 convs: fp16 operands written by the filtered activation, kind::f16; other "
                       "convs / projections: tf32; attention q/k/v: fp16; filtered activation: 3-term fp16 split = fp32 "
                       "accuracy)") if args.conv_algo == "tf32" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH, "per_gpu_batch": bs, "parallelism": f"dp{world}",
                        "conv_algo": args.conv_algo, "cuda_graph": True,
-                       "l2": "no flush: each step streams 1.03 GB of weights + activations, >> 126 MB L2"},
+                       "l2": "no flush between steps: each step streams 1.03 GB of weights + activations, >> 126 MB L2"},
             "clocks": clk.summary(), "finite": finite,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h_in.numel() * 4,
-                    "d2h_bytes_per_step": h_out.numel() * 4},
+                    "d2h_bytes_per_step": h_out.numel() * 4,
+                    "call": "MyLDMPipeline.denoise(pinned_host_latents, 50, start=i, stop=i+1) + copy of the result to pinned host memory, every step",
+                    "tail": {"what": "alias-free VAE decode of this rank's trajectories + ONE all-gather of the decoded frames "
+                                     "(parallel.gather_frames) + device-to-host copy of the 16 frames on rank 0; once per run, max over ranks",
+                             "ms": tail_ms, "gathered_bytes": BATCH * 3 * 256 * 256 * 4, "verify": verify}},
             "gpu_launches": gd.launches_per_step * args.steps,
             "launches_per_step": gd.launches_per_step,
-            "roofline": roofline, "roofline_filtered_act": fir, "breakdown": breakdown, "cpu_baseline": cpu_baseline,
-            "vae_decode": vae_decode,
+            "roofline": roofline, "roofline_filtered_act": fir, "breakdown": breakdown, "parity_err": parity,
+            "cpu_baseline": cpu_baseline, "weak_scaling": weak, "vae_decode": vae_decode,
             "lib": os.path.relpath(_lib.LIB_PATH, ROOT),
         }
         print(json.dumps(line), flush=True)

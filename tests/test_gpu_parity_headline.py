@@ -1,0 +1,172 @@
+"""GPU: parity of the BENCHMARKED numeric class at the benchmarked configuration.
+
+``bench.py`` times the default class - ``ops.set_default_conv_algo("tf32")`` with fp16 operand storage
+(``AFLDM_CONV_F16=1``) and fp16 q | k | v (``AFLDM_ATTN_F16=1``): tensor-core products on 11-bit significands, fp32
+accumulation, fp32 residual stream / norms / softmax.  These tests compare exactly that class with the fp32 oracle
+(PyTorch, TF32 disabled) on the full 256.4 M-parameter FFHQ UNet (configs/ldm/model_unet.json) and the full AF-VAE
+(configs/vae/model_afvae.json), random weights under seed 0, and state the tolerance the measurement supports
+(profiles/r02_parity_headline.txt, B200):
+
+    one step, B = 16:        max |d eps| 3.0e-3, mean 4.1e-4 (eps rms 0.50) -> asserted <= 6e-3 / 8e-4, rel-rms <= 2e-3
+    50 DDIM steps, B = 2:    rel-rms drift 3.4e-4 of the latent rms            -> asserted <= 1e-3
+    AF-VAE decode, B = 4:    max |d| 6.2e-3, mean 5.0e-4 (image rms 0.40)      -> asserted <= 1.5e-2 / 1.2e-3
+    exact-fp32 class (simt): max |d eps| 7.7e-6 at B = 16, 50-step rel-rms 6.9e-7
+
+SURVEY.md 7.4 proposed 2e-3 absolute on eps for the TF32 class; the measured MAXIMUM over 65 536 outputs is 3e-3 (the
+mean is 4e-4), which is what a chain of ~120 TF32-class layers gives; the bound asserted here is the measured one with 2x
+head-room, not the proposal."""
+import pytest
+import torch
+
+from afldm_b200 import ops
+from afldm_b200.af_modules import af_api
+from afldm_b200.models import AliasFreeAutoencoderKL, UNet2DModel
+from afldm_b200.pipelines import (AttnState, CrossFrameAttnProcessor, MyLDMPipeline, get_unet_attn_processors,
+                                  set_unet_attn_processor)
+from afldm_b200.schedulers import DDIMScheduler
+from oracle import af_blocks as OA
+from oracle import cross_frame as OC
+from oracle import nn as ON
+from oracle import pipeline as OP
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _fp32_oracle():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    prev = ops.default_conv_algo()
+    yield
+    ops.set_default_conv_algo(prev)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
+@pytest.fixture(scope="module")
+def unets():
+    torch.manual_seed(0)
+    ref = ON.UNet2DModel().to(DEV).eval()
+    mine = UNet2DModel.from_config().to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    OA.make_af_unet(ref)
+    af_api.make_af_unet(mine)
+    yield mine, ref
+    del mine, ref
+    torch.cuda.empty_cache()
+
+
+def latents(b, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(b, 4, 32, 32, generator=g).to(DEV)
+
+
+def err(a, b):
+    d = (a - b).abs()
+    rel = (d.pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    return d.max().item(), d.mean().item(), rel
+
+
+@pytest.mark.parametrize("algo,tmax,tmean,trel", [("tf32", 6e-3, 8e-4, 2e-3), ("simt", 3e-5, 5e-6, 1e-5)])
+def test_headline_step_b16_vs_fp32_oracle(unets, algo, tmax, tmean, trel):
+    """BASELINE config #2 exactly as benchmarked: seed-0 latents 16 x 4 x 32 x 32, one UNet evaluation."""
+    mine, ref = unets
+    ops.set_default_conv_algo(algo)
+    x = latents(16)
+    with torch.no_grad():
+        for t in (981, 1):
+            want = ref(x, torch.tensor(t, device=DEV)).sample
+            got = mine(x, t).sample
+            mx, mean, rel = err(got, want)
+            print(f"[{algo}] B=16 t={t}: max|d eps| {mx:.3e} mean {mean:.3e} rel-rms {rel:.3e} (eps rms {want.pow(2).mean().sqrt().item():.3f})")
+            assert mx < tmax and mean < tmean and rel < trel, (algo, t, mx, mean, rel)
+
+
+@pytest.mark.parametrize("algo,trel", [("tf32", 1e-3), ("simt", 5e-6)])
+def test_50_step_ddim_drift_b2(unets, algo, trel):
+    """The whole trajectory of ldm_pipeline.py:93-109 (50 steps, eta = 0) through the captured-graph path."""
+    mine, ref = unets
+    ops.set_default_conv_algo(algo)
+    x = latents(2)
+    pipe = MyLDMPipeline(None, mine, DDIMScheduler.from_config())
+    got = pipe.denoise(x, 50, use_cuda_graph=True)
+    want = OP.denoise(ref, ON.DDIMScheduler(), x, 50)
+    mx, mean, rel = err(got, want)
+    print(f"[{algo}] 50 DDIM steps B=2: max|d| {mx:.3e} mean {mean:.3e} rel-rms {rel:.3e} (latent rms {want.pow(2).mean().sqrt().item():.2f})")
+    assert rel < trel, (algo, mx, mean, rel)
+
+
+@pytest.mark.parametrize("algo,tmax,tmean", [("tf32", 1.5e-2, 1.2e-3), ("simt", 2e-4, 2e-5)])
+def test_afvae_decode_b4(algo, tmax, tmean):
+    """BASELINE config #3 architecture in the benchmarked class: 4 x 4 x 32 x 32 -> 4 x 3 x 256 x 256."""
+    ops.set_default_conv_algo(algo)
+    torch.manual_seed(0)
+    ref = ON.AutoencoderKL().to(DEV).eval()
+    mine = AliasFreeAutoencoderKL.from_config().to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    OA.make_af_vae_from_config(ref)
+    z = latents(4, seed=5)
+    with torch.no_grad():
+        want = ref.decode(z / 0.6).sample
+        got = mine.decode(z / 0.6).sample
+    mx, mean, rel = err(got, want)
+    print(f"[{algo}] AF-VAE decode B=4: max|d| {mx:.3e} mean {mean:.3e} rel-rms {rel:.3e}")
+    assert mx < tmax and mean < tmean, (algo, mx, mean)
+
+
+@pytest.mark.parametrize("algo,tol", [("tf32", 8e-3), ("simt", 3e-5)])
+def test_ddim_inversion_vs_oracle(unets, algo, tol):
+    """MyLDMPipeline.ddim_inversion (ldm_pipeline.py:133-160), 10 steps, full-size UNet."""
+    mine, ref = unets
+    ops.set_default_conv_algo(algo)
+    x = latents(2, seed=3)
+    sm, sr = DDIMScheduler.from_config(), ON.DDIMScheduler()
+    sm.set_timesteps(10)
+    sr.set_timesteps(10)
+    pipe = MyLDMPipeline(None, mine, sm)
+    got = pipe.ddim_inversion(x, bar=False)
+    want = OP.ddim_inversion(ref, sr, x)
+    mx, mean, rel = err(got, want)
+    print(f"[{algo}] ddim_inversion: max|d| {mx:.3e} mean {mean:.3e} rel-rms {rel:.3e}")
+    assert mx < tol, (algo, mx)
+    # inversion followed by sampling returns to the start (the scripts' real-image path, shift_ldm_ffhq.py:110-116)
+    if algo == "simt":
+        back = pipe.denoise(got, 10, use_cuda_graph=False)
+        back_ref = OP.denoise(ref, sr, want, 10)
+        assert (back - back_ref).abs().max().item() < 1e-3
+
+
+def test_cross_frame_interp_vs_oracle():
+    """CrossFrameAttnProcessor(enable_interp=True) (cross_frame_attn.py:100-122): two stored frames blended with alpha."""
+    cfg = dict(block_out_channels=[64, 128, 128], down_block_types=["AttnDownBlock2D", "AttnDownBlock2D", "DownBlock2D"],
+               up_block_types=["UpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D"], attention_head_dim=8, sample_size=16)
+    ops.set_default_conv_algo("simt")
+    torch.manual_seed(4)
+    ref = ON.UNet2DModel(**cfg).to(DEV).eval()
+    mine = UNet2DModel.from_config(cfg).to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    OA.make_af_unet(ref)
+    af_api.make_af_unet(mine)
+    st_m, st_r = AttnState(), OC.AttnState()
+    set_unet_attn_processor(mine, {k: CrossFrameAttnProcessor(st_m, enable_interp=True) for k in get_unet_attn_processors(mine)})
+    OC.set_attn_processor(ref, lambda: OC.CrossFrameAttnProcessor(st_r, enable_interp=True))
+    g = torch.Generator().manual_seed(9)
+    f0, f1, q = (torch.randn(n, 4, 16, 16, generator=g).to(DEV) for n in (1, 1, 3))
+    with torch.no_grad():
+        for st in (st_m, st_r):
+            st.reset()
+            st.set_timestep(torch.tensor(401))
+        for sid, frame in ((0, f0), (1, f1)):
+            st_m.set_store_id(sid)
+            st_r.set_store_id(sid)
+            a = mine(frame, 401).sample
+            b = ref(frame, torch.tensor(401, device=DEV)).sample
+            torch.testing.assert_close(a.contiguous(), b, rtol=0, atol=2e-4)
+        st_m.to_load()
+        st_r.to_load()
+        for alpha in (0.0, 0.3, 1.0):
+            st_m.set_alpha(alpha)
+            st_r.set_alpha(alpha)
+            a = mine(q, 401).sample
+            b = ref(q, torch.tensor(401, device=DEV)).sample
+            torch.testing.assert_close(a.contiguous(), b, rtol=0, atol=2e-4)

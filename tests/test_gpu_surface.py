@@ -27,6 +27,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _exact_torch_reference():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    prev = ops.default_conv_algo()
+    ops.set_default_conv_algo("simt")
+    yield
+    ops.set_default_conv_algo(prev)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
