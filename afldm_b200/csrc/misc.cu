@@ -217,6 +217,23 @@ axpby_dev_kernel(const float* __restrict__ x, const float* __restrict__ e, float
         out[i] = fmaf(cx, x[i], ce * e[i]);
 }
 
+// ------------------------------------------------------------------ slot copy (cross-frame attention maps)
+// table[slot][n] <-> buf[n] with the slot index read from DEVICE memory: a captured denoising step can keep one map per
+// timestep (CrossFrameAttnProcessor, afldm/pipelines/cross_frame_attn.py:78-97, keys its dictionaries by the host value
+// t.item(); here the step index is a device scalar refreshed between graph replays).
+__global__ void __launch_bounds__(256)
+slot_copy_kernel(float* __restrict__ table, float* __restrict__ buf, long long n4, const int* __restrict__ slot, int store) {
+    pdl_trigger();
+    pdl_wait();
+    float4* t4 = reinterpret_cast<float4*>(table) + (long long)slot[0] * n4;
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        if (store) t4[i] = b4[i];
+        else b4[i] = t4[i];
+    }
+}
+
 // ------------------------------------------------------------------ upfirdn2d (NCHW)
 // out[oy][ox] = gain * sum_{fy,fx} f'[fy][fx] * xup[oy*downy + fy - pady0][ox*downx + fx - padx0]
 // where xup is x zero-stuffed by (upy, upx) and f' = f flipped unless `flip`
@@ -413,6 +430,13 @@ extern "C" int afldm_axpby_dev_f32(const float* x, const float* eps, float* out,
                                    long long n, afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || coef == nullptr || n <= 0) return AFLDM_E_ARG;
     launch_k(axpby_dev_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, eps, out, coef, n);
+    return launched();
+}
+
+extern "C" int afldm_slot_copy_f32(float* table, float* buf, long long n, const int* slot, int store, afldm_stream_t stream) {
+    if (table == nullptr || buf == nullptr || slot == nullptr || n <= 0 || (n & 3) != 0) return AFLDM_E_ARG;
+    if (!aligned16(table) || !aligned16(buf)) return AFLDM_E_ARG;
+    launch_k(slot_copy_kernel, dim3(grid_for(n / 4)), dim3(256), 0, as_stream(stream), table, buf, n / 4, slot, store);
     return launched();
 }
 

@@ -777,6 +777,20 @@ def axpby(x: torch.Tensor, e: torch.Tensor, cx, ce, out: Optional[torch.Tensor] 
     return out
 
 
+def slot_copy(table: torch.Tensor, buf: torch.Tensor, slot: torch.Tensor, store: bool) -> None:
+    """``table[slot] = buf`` (store) or ``buf = table[slot]`` with ``slot`` a DEVICE int32 scalar - graph-capturable
+    per-timestep storage of the cross-frame attention maps (cross_frame_attn.py:78-97)."""
+    _chk(table, "table")
+    _chk(buf, "buf")
+    if slot.dtype != torch.int32 or not slot.is_cuda or table.ndim < 2 or table[0].numel() != buf.numel():
+        raise _lib.AfldmError("slot_copy: table [slots, ...] / buf of one slot / device int32 slot expected")
+    n = buf.numel()
+    L = _lib.lib()
+    _run("slot_copy", dict(elems=n),
+         lambda: L.afldm_slot_copy_f32(table.data_ptr(), buf.data_ptr(), n, slot.data_ptr(), int(bool(store)), _stream()),
+         (table, buf, slot))
+
+
 def upfirdn2d(x: torch.Tensor, f: torch.Tensor, up=1, down=1, padding=(0, 0, 0, 0), flip_filter=False,
               gain=1.0) -> torch.Tensor:
     """StyleGAN3 upfirdn2d on NCHW x (upfirdn2d.py:118-162); padding = (x0, x1, y0, y1); f 1-D or 2-D."""

@@ -263,32 +263,44 @@ def aggregate(table):
     return agg
 
 
-def rooflines(agg, pk):
-    """Roofline of the dominant kernel family (by cold device time) and of the filtered activation (the kernel the north
-    star names).  Kernels are timed alone -> burst peaks (MEASURED_PEAKS.json), per the bench contract."""
-    top_name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
+def rooflines(agg, pk, step_ms=None):
+    """Roofline of the dominant kernel family and of the filtered activation (the kernel the north star names).
+    `achieved` uses the family's time INSIDE the step: its back-to-back (L2-hot) device time scaled by
+    step_ms / sum(hot times), i.e. the measured step with the inter-kernel gaps shared out pro rata (the hot times sum
+    to within a few percent of the step; ncu's per-launch shares agree, profiles/) -> the SUSTAINED peaks apply.
+    The cold figure (each launch alone after an L2 flush, burst peak) is reported beside it as the pessimistic bracket."""
+    hot_total = sum(a["ms_hot"] for a in agg.values())
+    scale = (step_ms / hot_total) if step_ms else 1.0
+    top_name, a = max(agg.items(), key=lambda kv: kv[1]["ms_hot"])
+    t_in = a["ms_hot"] * scale
     if a["flops"] > 0:
-        ach = a["flops"] / (a["ms"] / 1e3) / 1e12
-        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16"], "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"],
-                "avg_launch_ms": a["ms"] / a["launches"], "achieved_l2_hot": a["flops"] / (a["ms_hot"] / 1e3) / 1e12,
-                "peak_source": pk["source"] + ": bf16 burst figure (each launch is timed alone, after an L2 flush); "
+        ach = a["flops"] / (t_in / 1e3) / 1e12
+        cold = a["flops"] / (a["ms"] / 1e3) / 1e12
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_sustained"], "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"],
+                "avg_launch_ms": t_in / a["launches"], "ms_per_step_in_step": t_in,
+                "cold_l2": {"achieved": cold, "peak": pk["bf16"], "frac": cold / pk["bf16"], "ms_per_step": a["ms"],
+                            "what": "each launch timed alone with CUDA events after an L2 flush; burst peak"},
+                "peak_source": pk["source"] + ": bf16 sustained figure (the family's time is taken inside the step: L2-hot "
+                               "device time x step_ms / sum of hot times); "
                                + ("operands are fp16 (tcgen05.mma.kind::f16), the same tensor rate as bf16"
                                   if top_name == "conv2d_f16" else "operands are TF32, whose tensor peak is half the bf16 peak"),
                 "algorithmic_flops_per_step": a["flops"],
                 "traffic_unit": "DRAM bytes per launch, average over the conv_tc_kernel family of one step (ncu, profiles/)"}
     else:
-        ach = a["bytes"] / (a["ms"] / 1e3) / 1e9
+        ach = a["bytes"] / (t_in / 1e3) / 1e9
         roof = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"], "avg_launch_ms": a["ms"] / a["launches"],
-                "peak_source": pk["source"] + " (copy bandwidth; each launch timed alone, after an L2 flush)"}
+                "traffic": ncu_traffic(top_name), "launches_per_step": a["launches"], "avg_launch_ms": t_in / a["launches"],
+                "peak_source": pk["source"] + " (copy bandwidth)"}
     fir = None
     fa = agg.get("filtered_act")
     if fa:
-        ach = fa["bytes"] / (fa["ms"] / 1e3) / 1e9
+        t_in = fa["ms_hot"] * scale
+        ach = fa["bytes"] / (t_in / 1e3) / 1e9
+        cold = fa["bytes"] / (fa["ms"] / 1e3) / 1e9
         fir = {"kernel": "filtered_act", "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-               "achieved_l2_hot": fa["bytes"] / (fa["ms_hot"] / 1e3) / 1e9, "launches_per_step": fa["launches"],
-               "ms_per_step": fa["ms"], "ms_per_step_l2_hot": fa["ms_hot"],
+               "launches_per_step": fa["launches"], "ms_per_step_in_step": t_in,
+               "cold_l2": {"achieved": cold, "frac": cold / pk["hbm"], "ms_per_step": fa["ms"]},
                "algorithmic_bytes_per_step": fa["bytes"], "traffic": ncu_traffic("filtered_act"),
                "floors": "HBM by bytes; the formulation's own floors on B200 are 2 MUFU per SiLU on the 4x plane and "
                          "(tcgen05 form) 57 B/clk/SM of TMEM reads - DESIGN.md section 3"}
@@ -394,10 +406,11 @@ def time_vae_decode(torch, dev, batch, pk, contract=False):
             res["h2d_bytes"], res["d2h_bytes"] = h_in.numel() * 4, h_out.numel() * 4
             table = time_records(records, torch, dev, reps=3)
             agg = aggregate(table)
-            res["roofline"], res["roofline_filtered_act"] = rooflines(agg, pk)
-            tot = sum(a["ms"] for a in agg.values())
-            res["breakdown"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4)}
-                                for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+            res["roofline"], res["roofline_filtered_act"] = rooflines(agg, pk, step_ms=ms)
+            tot = sum(a["ms_hot"] for a in agg.values())
+            res["breakdown"] = {k: {"launches": v["launches"], "ms": round(v["ms_hot"], 3), "ms_cold_l2": round(v["ms"], 3),
+                                    "share": round(v["ms_hot"] / tot, 4)}
+                                for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms_hot"])}
     del vae, out, g
     torch.cuda.empty_cache()
     return res
@@ -499,8 +512,8 @@ def run_i2sb_workload(args, torch, dev):
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
     pk = peaks()
     agg = aggregate(time_records(records, torch, dev, reps=3))
-    roof, fir = rooflines(agg, pk)
-    tot = sum(a["ms"] for a in agg.values())
+    roof, fir = rooflines(agg, pk, step_ms=ms)
+    tot = sum(a["ms_hot"] for a in agg.values())
     line = {"metric": "i2sb_unet_steps_per_sec", "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "TF32 class (see the headline line)", "data": "synthetic",
@@ -511,8 +524,8 @@ def run_i2sb_workload(args, torch, dev):
             "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h_in.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4},
             "gpu_launches": gd.launches_per_step * args.steps, "launches_per_step": gd.launches_per_step,
             "roofline": roof, "roofline_filtered_act": fir,
-            "breakdown": {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4)}
-                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+            "breakdown": {k: {"launches": v["launches"], "ms": round(v["ms_hot"], 3), "share": round(v["ms_hot"] / tot, 4)}
+                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms_hot"])},
             "cpu_baseline": None}
     print(json.dumps(line), flush=True)
 
@@ -764,9 +777,12 @@ def main():
         if args.dump_breakdown:
             dump_breakdown(args.dump_breakdown, table)
         total_iso = sum(a["ms"] for a in agg.values())
-        breakdown = {k: {"launches": v["launches"], "ms_per_step": round(v["ms"], 4), "ms_per_step_l2_hot": round(v["ms_hot"], 4),
-                         "share": round(v["ms"] / total_iso, 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
-        roofline, fir = rooflines(agg, pk)
+        total_hot = sum(a["ms_hot"] for a in agg.values())
+        breakdown = {k: {"launches": v["launches"], "ms_per_step": round(v["ms_hot"], 4), "ms_per_step_cold_l2": round(v["ms"], 4),
+                         "share": round(v["ms_hot"] / total_hot, 4)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms_hot"])}
+        breakdown["_note"] = ("ms_per_step: back-to-back launches of the same call (L2-hot), sum %.3f ms vs the measured step %.3f ms; "
+                              "ms_per_step_cold_l2: each launch alone after an L2 flush, sum %.3f ms" % (total_hot, ms_max / args.steps, total_iso))
+        roofline, fir = rooflines(agg, pk, step_ms=ms_max / args.steps)
 
     parity = None
     if rank == 0 and world == 1 and not args.no_parity:

@@ -250,6 +250,15 @@ AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, 
 AFLDM_API int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
                                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
 
+/* ---- cross-frame attention map store (afldm/pipelines/cross_frame_attn.py:78-97) -------------
+ * CrossFrameAttnProcessor keeps, per attention layer, the layer input of the reference frame for every timestep
+ * (`self.maps[store_id][t] = hidden_states`, keyed by the HOST value t.item() :31-33) and feeds it back as the K / V source
+ * of later frames.  Here the maps of a layer are one device table [slots][n] and the slot (= step index) is read from
+ * device memory, so STORE and LOAD passes can live in a captured CUDA graph:
+ *   store != 0: table[*slot][0..n) = buf[0..n);   store == 0: buf[0..n) = table[*slot][0..n).
+ * n % 4 == 0, 16-byte aligned pointers; the caller guarantees 0 <= *slot < slots. */
+AFLDM_API int afldm_slot_copy_f32(float* table, float* buf, long long n, const int* slot, int store, afldm_stream_t stream);
+
 /* ---- fractional shift (the equivariance measurement's warp) ---------------------------------
  * ImageShifter('ideal' | 'ideal_crop', r).shift(img, ti, tj) (afldm/shift_utils/shifters.py:157-191):
  * UpsampleRFFT(r) -> torch.roll by (round(ti r), round(tj r)) -> validity mask (gen_valid_mask :31-49) ->
