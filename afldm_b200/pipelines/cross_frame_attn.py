@@ -17,14 +17,38 @@ from .. import ops
 from ..models.blocks import AttnProcessor2_0
 
 
+class SlotContext:
+    """Device-side addressing of the stored maps for captured steps: ``slot`` (int32 scalar on the device) is the index
+    of the current step; every processor keeps its maps in one table [num_slots, ...] and moves them with
+    ``ops.slot_copy`` (``afldm_slot_copy_f32``), so neither the STORE nor the LOAD pass reads a host value."""
+
+    def __init__(self, num_slots: int, device):
+        self.num_slots = int(num_slots)
+        self.slot = torch.zeros(1, dtype=torch.int32, device=device)
+        self._index = torch.arange(self.num_slots, dtype=torch.int32, device=device)
+
+    def set_slot(self, i: int) -> None:
+        self.slot.copy_(self._index[i:i + 1])             # device-to-device: legal between graph replays
+
+
 class AttnState:
     STORE, LOAD, IDLE = 0, 1, 2
 
     def __init__(self):
+        self.slots = None
         self.reset()
 
     def reset(self):
         self._state, self._timestep, self._store_id, self._alpha = AttnState.STORE, 0, 0, 0
+
+    def enable_slots(self, num_slots: int, device) -> "SlotContext":
+        """Switch the processors that share this state to step-indexed device tables (one slot per denoising step)
+        instead of dictionaries keyed by ``t.item()`` - the form a captured CUDA graph can replay."""
+        self.slots = SlotContext(num_slots, device)
+        return self.slots
+
+    def disable_slots(self) -> None:
+        self.slots = None
 
     state = property(lambda self: self._state)
     timestep = property(lambda self: self._timestep)
@@ -52,6 +76,26 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
         self.attn_state = attn_state
         self.maps = [dict(), dict()]
         self.enable_interp = enable_interp
+        self._tables = [None, None]        # slot mode: [num_slots, n, H, W, C] per store_id
+        self._stage = [None, None]         # slot mode: the map of the current step, copied out of the table
+
+    def _slot_store(self, store_id: int, x_nhwc: torch.Tensor) -> None:
+        ctx = self.attn_state.slots
+        tab = self._tables[store_id]
+        if tab is None or tab.shape[1:] != x_nhwc.shape or tab.shape[0] != ctx.num_slots or tab.device != x_nhwc.device:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("cross-frame map table would be allocated during CUDA-graph capture: warm up first")
+            tab = self._tables[store_id] = torch.empty((ctx.num_slots,) + tuple(x_nhwc.shape), dtype=torch.float32,
+                                                       device=x_nhwc.device)
+            self._stage[store_id] = torch.empty(tuple(x_nhwc.shape), dtype=torch.float32, device=x_nhwc.device)
+        ops.slot_copy(tab, x_nhwc.contiguous(), ctx.slot, store=True)
+
+    def _slot_load(self, store_id: int) -> torch.Tensor:
+        tab, stage = self._tables[store_id], self._stage[store_id]
+        if tab is None:
+            raise RuntimeError("cross-frame attention: LOAD before any STORE pass")
+        ops.slot_copy(tab, stage, self.attn_state.slots.slot, store=False)
+        return stage.view(stage.shape[0], stage.shape[1] * stage.shape[2], stage.shape[3])      # [n, HW, C]
 
     @staticmethod
     def _kv_source(attn, stored: torch.Tensor) -> torch.Tensor:
@@ -75,12 +119,18 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
         if encoder_hidden_states is not None or st.state == AttnState.IDLE:
             return plain(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
         t = st.timestep
+        slotted = st.slots is not None
         if st.state == AttnState.STORE:
-            self.maps[st.store_id][t] = hidden_states.detach()
+            if slotted:
+                self._slot_store(st.store_id, ops.nhwc(hidden_states))
+            else:
+                self.maps[st.store_id][t] = hidden_states.detach()
             return plain(attn, hidden_states, None, attention_mask, temb)
-        res = plain(attn, hidden_states, self._kv_source(attn, self.maps[0][t]), attention_mask, temb)
+        map0 = self._slot_load(0) if slotted else self.maps[0][t]
+        res = plain(attn, hidden_states, self._kv_source(attn, map0), attention_mask, temb)
         if self.enable_interp:                                 # morphing between two stored frames (:100-122)
-            res2 = plain(attn, hidden_states, self._kv_source(attn, self.maps[1][t]), attention_mask, temb)
+            map1 = self._slot_load(1) if slotted else self.maps[1][t]
+            res2 = plain(attn, hidden_states, self._kv_source(attn, map1), attention_mask, temb)
             a = float(st.alpha)
             r1, r2 = ops.nhwc(res), ops.nhwc(res2)
             res = ops.nchw_view(ops.axpby(r1, r2, 1.0 - a, a))

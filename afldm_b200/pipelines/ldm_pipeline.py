@@ -42,16 +42,47 @@ def graph_signature(unet) -> tuple:
     ``packing`` are rebuilt from them, and the capture holds raw pointers to those copies), the attention processors,
     the convolution algorithm and the feature switches.  ``MyLDMPipeline.graphed`` re-captures when it changes."""
     params = tuple((p.data_ptr(), p._version) for p in unet.parameters())
-    procs = tuple(id(m.get_processor()) for m in unet.modules() if hasattr(m, "get_processor"))
+    procs = []
+    for m in unet.modules():
+        if hasattr(m, "get_processor"):
+            pr = m.get_processor()
+            st = getattr(pr, "attn_state", None)
+            procs.append((id(pr), None if st is None else (st.state, st.store_id, id(st.slots),
+                                                           bool(getattr(pr, "enable_interp", False)))))
+    procs = tuple(procs)
     return (params, procs, ops.default_conv_algo(), ops.F16_CONV, ops.F16_ATTENTION, ops.FUSE_GN_PROLOGUE,
             ops.FUSE_CONCAT, ops.SHORTCUT_SIDE_STREAM)
 
 
+def _cfa_mode(unet):
+    """(state, store_id) of the cross-frame processors installed on the UNet, None for the default processors."""
+    for m in unet.modules():
+        if hasattr(m, "get_processor"):
+            st = getattr(m.get_processor(), "attn_state", None)
+            if st is not None:
+                return (st.state, st.store_id)
+    return None
+
+
 def graph_capturable(unet) -> bool:
-    """The captured step covers the default attention processors only: a ``CrossFrameAttnProcessor`` keys host-side
-    dictionaries by timestep and (in STORE state) would keep pointers into the graph's private memory pool."""
+    """The captured step covers the default attention processors, and ``CrossFrameAttnProcessor`` in slot mode
+    (``AttnState.enable_slots``): in its reference form the processor keys host-side dictionaries by ``t.item()`` and (in
+    STORE state) would keep pointers into the graph's private memory pool."""
     from ..models.blocks import AttnProcessor2_0
-    return all(type(m.get_processor()) is AttnProcessor2_0 for m in unet.modules() if hasattr(m, "get_processor"))
+    from .cross_frame_attn import AttnState, CrossFrameAttnProcessor
+    for m in unet.modules():
+        if not hasattr(m, "get_processor"):
+            continue
+        pr = m.get_processor()
+        if type(pr) is AttnProcessor2_0:
+            continue
+        # a cross-frame processor is capturable in slot mode (device-indexed map tables), with a fixed interpolation
+        # weight of 0 / no interpolation (alpha is a host scalar baked into the capture)
+        if type(pr) is CrossFrameAttnProcessor and pr.attn_state.slots is not None and not pr.enable_interp \
+                and pr.attn_state.state in (AttnState.STORE, AttnState.LOAD):
+            continue
+        return False
+    return True
 
 
 class GraphedDenoiser:
@@ -113,6 +144,7 @@ class MyLDMPipeline:
         self._graphs = {}
         self._tables = {}
         self._graph_ok = None
+        self._sweep = {}
         self._bar = {}
 
     # ------------------------------------------------------------------ construction
@@ -163,6 +195,7 @@ class MyLDMPipeline:
             self.vae.to(device)
         self._graphs.clear()
         self._tables = {}
+        self._sweep = {}
         return self
 
     @property
@@ -185,6 +218,9 @@ class MyLDMPipeline:
         The check walks the module tree (~2 ms of host time): ``denoise`` runs it at the start of a trajectory
         (``start == 0``), not for every window of one."""
         key = batch if size in (None, self.unet.config.sample_size) else (batch, size)
+        mode = _cfa_mode(self.unet)
+        if mode is not None:
+            key = (key, mode)                      # STORE / LOAD passes of the cross-frame processors are different graphs
         g = self._graphs.get(key)
         if g is not None and check and g.signature != graph_signature(self.unet):
             g = None
@@ -213,7 +249,12 @@ class MyLDMPipeline:
             self._graph_ok = graph_capturable(self.unet)
         if not use_cuda_graph or not self._graph_ok:
             self.scheduler.set_timesteps(num_inference_steps)
-            for t in self.progress_bar(self.scheduler.timesteps[start:stop]):
+            slots, state = self._slot_context(), self._attn_state()
+            for i, t in zip(range(start, stop), self.progress_bar(self.scheduler.timesteps[start:stop])):
+                if slots is not None:
+                    slots.set_slot(i)
+                elif state is not None:
+                    state.set_timestep(int(t))          # dictionary mode keys the maps by timestep (shift_ldm_ffhq.py:96)
                 eps = self.unet(self.scheduler.scale_model_input(latents, t), int(t)).sample
                 latents = self.scheduler.step(eps, int(t), latents).prev_sample
             return ops.to_nchw_contiguous(ops.nhwc(latents))
@@ -223,12 +264,67 @@ class MyLDMPipeline:
             self._tables = {"key": key, "tt": None}
             self._tables["tt"], self._tables["coef"] = self.step_tables(num_inference_steps, latents.shape[0])
         tt, coefs = self._tables["tt"], self._tables["coef"]
+        slots = self._slot_context()
         g.x.copy_(ops.nhwc(latents))
         for i in self.progress_bar(range(start, stop)):
             g.t.copy_(tt[i])
             g.coef.copy_(coefs[i])
+            if slots is not None:
+                slots.set_slot(i)
             g.replay()
         return ops.to_nchw_contiguous(g.x)
+
+    def _attn_state(self):
+        for m in self.unet.modules():
+            if hasattr(m, "get_processor"):
+                st = getattr(m.get_processor(), "attn_state", None)
+                if st is not None:
+                    return st
+        return None
+
+    def _slot_context(self):
+        st = self._attn_state()
+        return None if st is None else st.slots
+
+    @torch.no_grad()
+    def shift_sweep(self, init_latent: torch.Tensor, shifts, num_inference_steps: int = 50, latent_shifter=None,
+                    use_cuda_graph: bool = True):
+        """The measurement loop of scripts/shift_ldm_ffhq.py:50-159 as TWO trajectories instead of 1 + len(shifts)
+        sequential ones: the reference pass (cross-frame attention in STORE state, batch 1) and ONE batched pass over
+        every shifted start latent (LOAD state; the stored maps of the single reference frame serve all of them, K / V
+        batch 1).  Both replay captured steps: the per-timestep maps live in device tables indexed by a device-side
+        step counter (``AttnState.enable_slots``), so there is no ``t.item()`` synchronisation and no host dictionary.
+
+        ``init_latent`` [1,C,H,W]; ``shifts`` a sequence of (ti, tj) in latent pixels; ``latent_shifter`` defaults to
+        ``ImageShifter('ideal_crop', 8)`` (:62).  Returns (denoised reference [1,C,H,W], denoised shifted [S,C,H,W],
+        shifted start latents [S,C,H,W], masks [S,C,H,W]); the original attention processors are restored (:153-157)."""
+        from ..shift_utils import ImageShifter
+        from .cross_frame_attn import (AttnState, CrossFrameAttnProcessor, get_unet_attn_processors,
+                                       set_unet_attn_processor)
+        if init_latent.shape[0] != 1:
+            raise ValueError("shift_sweep: one reference latent [1,C,H,W] expected")
+        dev = self.device
+        init_latent = init_latent.to(device=dev, dtype=torch.float32)
+        shifter = latent_shifter or ImageShifter("ideal_crop", 8)
+        prev = get_unet_attn_processors(self.unet)
+        cache = self._sweep.get(num_inference_steps)
+        if cache is None or cache[2] != tuple(prev.keys()):
+            state = AttnState()
+            state.enable_slots(num_inference_steps, dev)
+            cache = self._sweep[num_inference_steps] = (state, {k: CrossFrameAttnProcessor(state) for k in prev},
+                                                        tuple(prev.keys()))
+        state, procs, _ = cache
+        set_unet_attn_processor(self.unet, dict(procs))
+        try:
+            state.reset()                                           # STORE
+            base = self.denoise(init_latent, num_inference_steps, use_cuda_graph)
+            state.to_load()
+            shifted, masks = shifter.shift_batch(init_latent, list(shifts))          # [S,1,C,H,W]
+            shifted, masks = shifted[:, 0].contiguous(), masks[:, 0].contiguous()
+            outs = self.denoise(shifted, num_inference_steps, use_cuda_graph)
+        finally:
+            set_unet_attn_processor(self.unet, dict(prev))
+        return base, outs, shifted, masks
 
     @torch.no_grad()
     def __call__(self, batch_size: int = 1, generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,

@@ -581,13 +581,87 @@ def run_upfirdn2d_workload(args, torch, dev):
     print(json.dumps(line), flush=True)
 
 
+def run_shift_workload(args, torch, dev):
+    """The north-star driver's own workload (scripts/shift_ldm_ffhq.py:50-159): 1 reference trajectory (cross-frame
+    attention STORE) + 16 shifted trajectories (LOAD), 50 DDIM steps each, full FFHQ UNet.  Timed two ways on the same
+    kernels: the reference's flow (17 sequential B = 1 trajectories, processors keyed by t.item(), eager launches) and
+    MyLDMPipeline.shift_sweep (two captured passes: B = 1 STORE, B = 16 LOAD)."""
+    from afldm_b200 import ops
+    from afldm_b200.pipelines import (AttnState, CrossFrameAttnProcessor, MyLDMPipeline, get_unet_attn_processors,
+                                      set_unet_attn_processor)
+    from afldm_b200.shift_utils import ImageShifter
+    ops.set_default_conv_algo(args.conv_algo)
+    pipe = MyLDMPipeline.from_config(seed=0, with_vae=False).to(dev)
+    steps, nshift = 50, 16
+    g = torch.Generator().manual_seed(0)
+    init = torch.randn(1, 4, 32, 32, generator=g).to(dev)
+    shifts = [(0.0, (k + 1) / 8.0) for k in range(nshift)]                     # offsets i / 8 latent pixels (:129-131)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pipe.shift_sweep(init, shifts, steps)                                       # warm-up: capture both graphs
+    torch.cuda.synchronize()
+    n0 = _launches()
+    with ClockSampler(dev.index or 0) as clk:
+        ev0.record()
+        base, outs, shifted, masks = pipe.shift_sweep(init, shifts, steps)
+        ev1.record()
+        ev1.synchronize()
+    ms_sweep = ev0.elapsed_time(ev1)
+    launches = _launches() - n0
+    # the reference's flow on the same kernels
+    prev = get_unet_attn_processors(pipe.unet)
+    st = AttnState()
+    set_unet_attn_processor(pipe.unet, {k: CrossFrameAttnProcessor(st) for k in prev})
+    shifter = ImageShifter("ideal_crop", 8)
+    sch = pipe.scheduler
+
+    def denoise(x):
+        sch.set_timesteps(steps)
+        for t in sch.timesteps:
+            st.set_timestep(t.to(dev))                                          # t.item(): one sync per step, as in the reference
+            x = sch.step(pipe.unet(x, int(t)).sample, int(t), x).prev_sample
+        return x
+
+    with torch.no_grad():
+        st.reset()
+        denoise(init)                                                           # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.reset()
+        rb = denoise(init)
+        st.to_load()
+        routs = [denoise(shifter.shift(init, ti, tj)[0]) for ti, tj in shifts]
+        torch.cuda.synchronize()
+        ms_loop = (time.perf_counter() - t0) * 1e3
+    set_unet_attn_processor(pipe.unet, dict(prev))
+    diff = max((outs[k:k + 1] - routs[k]).abs().max().item() for k in range(nshift))
+    evals = (1 + nshift) * steps
+    line = {"metric": "shift_ldm_unet_evals_per_sec", "value": evals / (ms_sweep / 1e3), "unit": "trajectory-steps/s", "n_gpus": 1,
+            "steps": evals, "warmup": 1, "ms_per_step": ms_sweep / evals, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "TF32 class (see the headline line)", "data": "synthetic",
+            "config": {"workload": "scripts/shift_ldm_ffhq.py flow: 1 STORE + 16 LOAD trajectories x 50 DDIM steps, FFHQ AF-LDM UNet, "
+                                   "cross-frame attention, B=1 reference + one B=16 batched pass, captured steps",
+                       "l2": "1.03 GB of weights per step >> 126 MB L2"},
+            "clocks": clk.summary(), "finite": bool(torch.isfinite(outs).all().item()),
+            "sweep_ms": ms_sweep,
+            "gpu_launches": launches + steps * sum(g.launches_per_step for g in pipe._graphs.values()),
+            "launches_per_step": {str(k): g.launches_per_step for k, g in pipe._graphs.items()},
+            "sequential_reference_flow": {"what": "the same 17 trajectories the way the reference script runs them: sequential B=1, "
+                                                   "dict-keyed CrossFrameAttnProcessor (t.item() per step), eager launches, same kernels",
+                                          "ms": ms_loop, "value": evals / (ms_loop / 1e3), "speedup_of_batched_sweep": ms_loop / ms_sweep},
+            "max_abs_diff_batched_vs_sequential": diff,
+            "e2e": {"value": evals / (ms_sweep / 1e3), "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "latents are generated on the device by the script itself (randn_tensor(device=...), :118-123)"},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d"])
+    ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d", "shift_ldm"])
     ap.add_argument("--conv-algo", default=os.environ.get("AFLDM_CONV_ALGO", "tf32"), choices=["simt", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
@@ -617,7 +691,8 @@ def main():
         if rank != 0:
             return
         ops.set_default_conv_algo(args.conv_algo)
-        return {"vae_decode": run_vae_workload, "i2sb": run_i2sb_workload, "upfirdn2d": run_upfirdn2d_workload}[args.workload](args, torch, dev)
+        return {"vae_decode": run_vae_workload, "i2sb": run_i2sb_workload, "upfirdn2d": run_upfirdn2d_workload,
+                "shift_ldm": run_shift_workload}[args.workload](args, torch, dev)
     if world > 1:
         # NCCL prints its version banner to stdout when the communicator is created: route fd 1 to stderr around the
         # (eager, device_id=) initialisation and the first collective so that stdout carries ONE JSON line only

@@ -246,3 +246,48 @@ def test_full_ffhq_unet_step_vs_oracle():
         got = mine(x, 981).sample
     err = (got - want).abs().max().item()
     assert err < 5e-4 * max(1.0, want.abs().max().item()), err
+
+
+def test_shift_sweep_batched_graph_matches_sequential_reference_loop():
+    """MyLDMPipeline.shift_sweep (captured STORE pass + ONE batched, captured LOAD pass over all shifts, device-indexed
+    map tables) against the reference's own flow (scripts/shift_ldm_ffhq.py:85-151): dictionary-keyed processors, one
+    eager trajectory per shift."""
+    from afldm_b200.pipelines import get_unet_attn_processors
+    from afldm_b200.shift_utils import ImageShifter
+    mine, _ = _small_unets(seed=6)
+    pipe = MyLDMPipeline(None, mine, DDIMScheduler.from_config())
+    init = randn(1, 4, 16, 16, seed=30)
+    shifts = [(0.0, k / 8.0) for k in (1, 3, 8)] + [(0.5, -0.25)]
+    steps = 5
+    prev = get_unet_attn_processors(mine)
+    base, outs, shifted, masks = pipe.shift_sweep(init, shifts, steps)
+    assert outs.shape == (4, 4, 16, 16) and masks.shape == (4, 4, 16, 16)
+    assert get_unet_attn_processors(mine) == prev                        # processors restored (:153-157)
+    eager = pipe.shift_sweep(init, shifts, steps, use_cuda_graph=False)
+    for a, b in zip((base, outs), eager[:2]):
+        assert torch.equal(a, b)                                          # captured == eager, same kernels
+    again = pipe.shift_sweep(init, shifts, steps)                         # cached graphs / tables replay
+    assert torch.equal(again[1], outs)
+    # the reference's loop: dict-keyed maps, sequential B = 1 trajectories
+    st = AttnState()
+    set_unet_attn_processor(mine, {k: CrossFrameAttnProcessor(st) for k in prev})
+    shifter = ImageShifter("ideal_crop", 8)
+    sch = DDIMScheduler.from_config()
+
+    def denoise(x):
+        sch.set_timesteps(steps)
+        for t in sch.timesteps:
+            st.set_timestep(t)
+            x = sch.step(mine(x, int(t)).sample, int(t), x).prev_sample
+        return x.contiguous()
+
+    with torch.no_grad():
+        st.reset()
+        ref_base = denoise(init)
+        st.to_load()
+        torch.testing.assert_close(base, ref_base, rtol=0, atol=2e-5)
+        for k, (ti, tj) in enumerate(shifts):
+            x0, m = shifter.shift(init, ti, tj)
+            torch.testing.assert_close(shifted[k:k + 1], x0, rtol=0, atol=1e-6)
+            torch.testing.assert_close(outs[k:k + 1], denoise(x0), rtol=0, atol=5e-5)
+    set_unet_attn_processor(mine, dict(prev))
