@@ -217,6 +217,29 @@ axpby_dev_kernel(const float* __restrict__ x, const float* __restrict__ e, float
         out[i] = fmaf(cx, x[i], ce * e[i]);
 }
 
+// ------------------------------------------------------------------ GEGLU (SD-1.5 feed-forward)
+// diffusers GEGLU (BasicTransformerBlock.ff.net.0 of UNet2DConditionModel, reached through
+// afldm/pipelines/video_equiv_editing_pipeline.py:680-686): y[m][h] = p[m][h] * gelu(p[m][H + h]), exact (erf) GELU.
+__global__ void __launch_bounds__(256)
+geglu_kernel(const float* __restrict__ p, float* __restrict__ y, long long rows, int H) {
+    pdl_trigger();
+    pdl_wait();
+    const long long total4 = rows * (H / 4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const long long m = i / (H / 4);
+        const int h4 = (int)(i - m * (H / 4));
+        const float4 a = *reinterpret_cast<const float4*>(p + m * 2 * H + 4 * h4);
+        const float4 g = *reinterpret_cast<const float4*>(p + m * 2 * H + H + 4 * h4);
+        float4 o;
+        o.x = a.x * (0.5f * g.x * (1.0f + erff(g.x * 0.70710678118654752f)));
+        o.y = a.y * (0.5f * g.y * (1.0f + erff(g.y * 0.70710678118654752f)));
+        o.z = a.z * (0.5f * g.z * (1.0f + erff(g.z * 0.70710678118654752f)));
+        o.w = a.w * (0.5f * g.w * (1.0f + erff(g.w * 0.70710678118654752f)));
+        *reinterpret_cast<float4*>(y + m * H + 4 * h4) = o;
+    }
+}
+
 // ------------------------------------------------------------------ slot copy (cross-frame attention maps)
 // table[slot][n] <-> buf[n] with the slot index read from DEVICE memory: a captured denoising step can keep one map per
 // timestep (CrossFrameAttnProcessor, afldm/pipelines/cross_frame_attn.py:78-97, keys its dictionaries by the host value
@@ -430,6 +453,13 @@ extern "C" int afldm_axpby_dev_f32(const float* x, const float* eps, float* out,
                                    long long n, afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || coef == nullptr || n <= 0) return AFLDM_E_ARG;
     launch_k(axpby_dev_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, eps, out, coef, n);
+    return launched();
+}
+
+extern "C" int afldm_geglu_f32(const float* proj, float* y, long long rows, int H, afldm_stream_t stream) {
+    if (proj == nullptr || y == nullptr || rows <= 0 || H <= 0 || (H & 3) != 0) return AFLDM_E_ARG;
+    if (!aligned16(proj) || !aligned16(y)) return AFLDM_E_ARG;
+    launch_k(geglu_kernel, dim3(grid_for(rows * (H / 4))), dim3(256), 0, as_stream(stream), proj, y, rows, H);
     return launched();
 }
 

@@ -115,9 +115,11 @@ class ResnetBlock2D(nn.Module):
 
 
 class AttnProcessor2_0:
-    """diffusers AttnProcessor2_0 for the attention-block form (4-D input), CUDA kernels inside.
+    """diffusers AttnProcessor2_0, CUDA kernels inside.  Two input forms, as in diffusers: the attention-block form
+    (4-D [B,C,H,W]: group norm, biased projections, residual) and the transformer form (3-D [B,N,C]: SD-1.5
+    ``BasicTransformerBlock.attn1 / attn2``, bias-free q / k / v, no norm, no residual).
 
-    ``encoder_hidden_states`` ([Bkv, Nk, C], already normalised by the caller, as in
+    ``encoder_hidden_states`` ([Bkv, Nk, Ckv], already normalised by the caller, as in
     cross_frame_attn.py:86-97) supplies K/V; Bkv may divide B (each K/V batch serves B/Bkv queries
     batches without being tiled in memory)."""
 
@@ -126,12 +128,20 @@ class AttnProcessor2_0:
                  *args, **kwargs) -> torch.Tensor:
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is not used on the AF-LDM path")
-        x = ops.nhwc(hidden_states)
+        spatial = hidden_states.ndim == 4
+        if spatial:
+            x = ops.nhwc(hidden_states)
+        else:
+            x3 = hidden_states.contiguous()
+            x = x3.view(x3.shape[0], x3.shape[1], 1, x3.shape[2])          # tokens as an [N x 1] image
         b, h, w, c = x.shape
+        if attn.to_q.weight.shape[0] != c:
+            raise NotImplementedError("attention with inner_dim != query_dim")
         d = c // attn.heads
+        fast = d <= 64 and d % 8 == 0          # head dims the flash kernels cover (24 in the LDM UNet, 40 in SD-1.5)
         # TF32 class: the projections may hand q | k | v over as fp16 (same 11-bit significands as TF32 operands)
         # to the ldmatrix / mma.m16n8k16 attention kernel
-        f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and d <= 64 and d % 8 == 0
+        f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and fast
         # ... and then the normalised input and the attention output, each consumed by ONE projection, are stored as
         # fp16 too (kind::f16 projections: half the operand bytes)
         half = (f16 and encoder_hidden_states is None and attn.group_norm is not None
@@ -156,42 +166,46 @@ class AttnProcessor2_0:
             q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
         else:
             src = encoder_hidden_states
-            if src.ndim != 3 or src.shape[-1] != c:
-                raise ValueError("encoder_hidden_states must be [Bkv, Nk, C]")
+            if src.ndim != 3 or src.shape[-1] != attn.to_k.weight.shape[1]:
+                raise ValueError("encoder_hidden_states must be [Bkv, Nk, cross_attention_dim]")
             src = src.contiguous()
             wq, bq, _ = conv_params(attn.to_q)
             q = ops.conv2d(xn, wq, bq, 1).view(b, h * w, c)
             wkv, bkv = fused_linear_params(attn, "kv", (attn.to_k, attn.to_v))
-            kv = ops.conv2d(src.view(src.shape[0], src.shape[1], 1, c), wkv, bkv, 1).view(src.shape[0], src.shape[1], 2 * c)
+            kv = ops.conv2d(src.view(src.shape[0], src.shape[1], 1, src.shape[2]), wkv, bkv, 1)
+            kv = kv.view(src.shape[0], src.shape[1], 2 * c)
             k, v = kv[:, :, :c], kv[:, :, c:]
         if q.dtype == torch.float16 and k.dtype == torch.float16:
             o = ops.attention_f16(q, k, v, attn.heads, out_half=xn.dtype == torch.float16)
-        elif d <= 64 and d % 8 == 0:
+        elif fast:
             o = ops.attention(q, k, v, attn.heads)
         else:
             o = ops.attention_gemm(q, k, v, attn.heads)
         out = conv_after_act(o.view(b, h, w, c), attn.to_out[0], residual=x if attn.residual_connection else None,
-                             gn_stats=True)
+                             gn_stats=spatial)
         if attn.rescale_output_factor != 1.0:
             raise NotImplementedError("rescale_output_factor != 1")
-        return ops.nchw_view(out)
+        return ops.nchw_view(out) if spatial else out.view(b, h * w, c)
 
 
 class Attention(nn.Module):
-    """diffusers Attention in its attention-block configuration (bias, group norm, residual)."""
+    """diffusers Attention: the attention-block configuration (bias, group norm, residual; the default) or the
+    transformer configuration of SD-1.5 (``norm=False, residual=False, bias=False``, optional ``cross_attention_dim``)."""
 
-    def __init__(self, channels: int, heads: int, dim_head: int, groups: int = 32, eps: float = 1e-5):
+    def __init__(self, channels: int, heads: int, dim_head: int, groups: int = 32, eps: float = 1e-5,
+                 cross_attention_dim: Optional[int] = None, bias: bool = True, norm: bool = True, residual: bool = True):
         super().__init__()
         if heads * dim_head != channels:
             raise ValueError("heads * dim_head must equal channels")
         self.heads, self.dim_head = heads, dim_head
         self.scale = dim_head ** -0.5
-        self.residual_connection = True
+        self.residual_connection = residual
         self.rescale_output_factor = 1.0
-        self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True)
-        self.to_q = nn.Linear(channels, channels)
-        self.to_k = nn.Linear(channels, channels)
-        self.to_v = nn.Linear(channels, channels)
+        self.group_norm = nn.GroupNorm(groups, channels, eps=eps, affine=True) if norm else None
+        kv_dim = cross_attention_dim or channels
+        self.to_q = nn.Linear(channels, channels, bias=bias)
+        self.to_k = nn.Linear(kv_dim, channels, bias=bias)
+        self.to_v = nn.Linear(kv_dim, channels, bias=bias)
         self.to_out = nn.ModuleList([nn.Linear(channels, channels), nn.Dropout(0.0)])
         self.processor = AttnProcessor2_0()
 

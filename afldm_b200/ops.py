@@ -777,6 +777,27 @@ def axpby(x: torch.Tensor, e: torch.Tensor, cx, ce, out: Optional[torch.Tensor] 
     return out
 
 
+def geglu(proj: torch.Tensor) -> torch.Tensor:
+    """diffusers GEGLU on the projection [..., 2H] -> [..., H]: ``proj[..., :H] * gelu(proj[..., H:])`` (exact GELU)."""
+    _chk(proj, "proj")
+    h = proj.shape[-1] // 2
+    rows = proj.numel() // (2 * h)
+    y = torch.empty(proj.shape[:-1] + (h,), dtype=torch.float32, device=proj.device)
+    L = _lib.lib()
+    _run("geglu", dict(elems=y.numel()), lambda: L.afldm_geglu_f32(proj.data_ptr(), y.data_ptr(), rows, h, _stream()), (proj, y))
+    return y
+
+
+def layer_norm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """nn.LayerNorm over the last dim of [..., C] (SD-1.5 transformer blocks): every token is one "image" of one pixel for
+    the GroupNorm statistics kernel (groups = 1), the affine is the same per-channel gamma / beta."""
+    _chk(x, "x")
+    c = x.shape[-1]
+    tokens = x.numel() // c
+    y = groupnorm_act(x.view(tokens, 1, 1, c), 1, eps, weight, bias, act="identity")
+    return y.view(x.shape)
+
+
 def slot_copy(table: torch.Tensor, buf: torch.Tensor, slot: torch.Tensor, store: bool) -> None:
     """``table[slot] = buf`` (store) or ``buf = table[slot]`` with ``slot`` a DEVICE int32 scalar - graph-capturable
     per-timestep storage of the cross-frame attention maps (cross_frame_attn.py:78-97)."""

@@ -56,7 +56,9 @@ def fused_linear_params(owner: nn.Module, tag: str, layers: Sequence[nn.Module])
     cache = getattr(owner, name, None)
     if cache is None or cache[0] != key:
         w = torch.cat([m.weight.detach().reshape(m.weight.shape[0], -1) for m in layers], dim=0).contiguous()
-        b = torch.cat([m.bias.detach() for m in layers], dim=0).contiguous()
+        # bias-free projections (SD-1.5 transformer attention: to_q / to_k / to_v have no bias)
+        b = None if all(m.bias is None for m in layers) else torch.cat(
+            [m.bias.detach() if m.bias is not None else m.weight.new_zeros(m.weight.shape[0]) for m in layers], dim=0).contiguous()
         cache = (key, (w, b))
         object.__setattr__(owner, name, cache)
     return cache[1]

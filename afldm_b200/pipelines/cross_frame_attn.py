@@ -122,7 +122,9 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
         slotted = st.slots is not None
         if st.state == AttnState.STORE:
             if slotted:
-                self._slot_store(st.store_id, ops.nhwc(hidden_states))
+                hs = hidden_states
+                self._slot_store(st.store_id, ops.nhwc(hs) if hs.ndim == 4 else
+                                 hs.contiguous().view(hs.shape[0], hs.shape[1], 1, hs.shape[2]))
             else:
                 self.maps[st.store_id][t] = hidden_states.detach()
             return plain(attn, hidden_states, None, attention_mask, temb)

@@ -1,0 +1,209 @@
+"""Video editing with cross-frame attention on the alias-free SD-1.5 UNet: the call surface and loop structure of
+/root/reference/afldm/pipelines/video_equiv_editing_pipeline.py (``image2latent`` :214-226, ``ddim_inversion`` :174-211,
+``get_timesteps`` :319-327, ``__call__`` :330-748; driven by scripts/video_editing.py).
+
+Flow of ``__call__`` (:503-748): install ``CrossFrameAttnProcessor`` on every attention; per frame, VAE-encode and
+DDIM-invert it with the inversion prompt and NO guidance (frame 0 in STORE state, the others in LOAD state, :593-607);
+run the reverse pass of frame 0 with classifier-free guidance in STORE state to record its self-attention inputs
+(``save_activations`` :612-649); denoise every frame in LOAD state against those maps (:659-697); decode each frame
+(:721-727); restore the processors (:743).
+
+Differences, all on the host side: (1) the CLIP text encoder is outside this build, so the text conditions arrive as
+``prompt_embeds`` / ``negative_prompt_embeds`` / ``inv_prompt_embeds`` tensors [1, 77, 768] (or through a user-supplied
+``encode_prompt`` callable); (2) the reference evaluates the frames one by one (:668-692, B = 2 per call) - they are
+independent given the frame-0 maps, so ``frame_batch`` frames go through the UNet together ([uncond x F | cond x F]; the
+attention kernel reads K/V batch b // F, the same repeat the reference materialises, cross_frame_attn.py:91-97);
+(3) SDEdit initialisation (``use_sdedit``) is not provided.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..models.af_vae import AutoencoderKL
+from ..models.unet_2d_condition import UNet2DConditionModel
+from ..schedulers.ddim import DDIMScheduler
+from .cross_frame_attn import AttnState, CrossFrameAttnProcessor
+
+SD15_DDIM = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 steps_offset=1, set_alpha_to_one=False, clip_sample=False, prediction_type="epsilon",
+                 timestep_spacing="leading")
+SD15_VAE = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=[128, 256, 512, 512],
+                layers_per_block=2, scaling_factor=0.18215, sample_size=512)
+
+
+class StableDiffusionPipelineOutput:
+    def __init__(self, images, nsfw_content_detected=None):
+        self.images, self.nsfw_content_detected = images, nsfw_content_detected
+
+
+def _to_tensor(img) -> torch.Tensor:
+    """VaeImageProcessor.preprocess for one frame: PIL / uint8 array -> [1,3,H,W] in [-1, 1]; tensors pass ([0,1] -> [-1,1])."""
+    if isinstance(img, torch.Tensor):
+        t = img if img.ndim == 4 else img.unsqueeze(0)
+        return 2.0 * t - 1.0 if float(t.min()) >= 0.0 else t
+    arr = np.asarray(img)
+    t = torch.from_numpy(arr.astype(np.float32) / 255.0).permute(2, 0, 1).unsqueeze(0)
+    return 2.0 * t - 1.0
+
+
+class VideoEquivariantEditingPipeline:
+    def __init__(self, vae: AutoencoderKL, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
+                 encode_prompt: Optional[Callable[[str], torch.Tensor]] = None):
+        self.vae, self.unet, self.scheduler = vae, unet, scheduler
+        self.encode_prompt_fn = encode_prompt
+        self.attn_state = AttnState()
+        self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
+
+    @classmethod
+    def from_config(cls, unet_config=None, vae_config=None, scheduler_config=None, seed: int = 0, alias_free: bool = True):
+        """Randomly initialised pipeline of the SD-1.5 architecture (no checkpoint is reachable offline)."""
+        from ..af_modules.af_api import make_af_unet, make_af_vae_from_config
+        from ..models.unet_2d_condition import SD15_UNET
+        torch.manual_seed(seed)
+        unet = UNet2DConditionModel.from_config(unet_config or SD15_UNET)
+        vae = AutoencoderKL.from_config(vae_config or SD15_VAE)
+        if alias_free:
+            make_af_unet(unet)
+            make_af_vae_from_config(vae)
+        return cls(vae, unet, DDIMScheduler.from_config(scheduler_config or SD15_DDIM))
+
+    def to(self, device):
+        self.unet.to(device)
+        if self.vae is not None:
+            self.vae.to(device)
+        return self
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    # ------------------------------------------------------------------ pieces of the reference pipeline
+    @torch.no_grad()
+    def image2latent(self, image) -> torch.Tensor:
+        """:214-226: posterior MEAN of the VAE encoder, scaled."""
+        x = _to_tensor(image).to(device=self.device, dtype=torch.float32)
+        return self.vae.encode(x).latent_dist.mean * self.vae.config.scaling_factor
+
+    def get_timesteps(self, num_inference_steps: int, strength: float):
+        """:319-327."""
+        init_timestep = min(int(num_inference_steps * strength), num_inference_steps)
+        t_start = max(num_inference_steps - init_timestep, 0)
+        return self.scheduler.timesteps[t_start:], num_inference_steps - t_start
+
+    def _eps(self, latents: torch.Tensor, t: int, cond: torch.Tensor, guidance_scale: float, uncond: Optional[torch.Tensor]):
+        """UNet evaluation with classifier-free guidance: batch [uncond x F | cond x F] (:668-691)."""
+        f = latents.shape[0]
+        if uncond is None:
+            return self.unet(latents, t, encoder_hidden_states=cond.expand(f, -1, -1).contiguous()).sample
+        x2 = torch.cat([latents, latents], dim=0)
+        ehs = torch.cat([uncond.expand(f, -1, -1), cond.expand(f, -1, -1)], dim=0).contiguous()
+        e = ops.nhwc(self.unet(x2, t, encoder_hidden_states=ehs).sample)
+        eu, ec = e[:f], e[f:]
+        # eps = eu + s (ec - eu) = (1 - s) eu + s ec
+        return ops.nchw_view(ops.axpby(eu.contiguous(), ec.contiguous(), 1.0 - guidance_scale, guidance_scale))
+
+    @torch.no_grad()
+    def ddim_inversion(self, latent: torch.Tensor, timesteps, cond: torch.Tensor, scale: float = 1.0, bar: bool = False,
+                       attn_invert: bool = False, uncond: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """:174-211: deterministic DDIM run backwards over ``reversed(timesteps)``."""
+        sch = self.scheduler
+        ts = [int(t) for t in reversed(list(timesteps))]
+        latent = latent.to(device=self.device, dtype=torch.float32)
+        for i, t in enumerate(ts):
+            a_t = sch.alphas_cumprod[t]
+            a_prev = sch.alphas_cumprod[ts[i - 1]] if i > 0 else sch.final_alpha_cumprod
+            mu, mu_prev = a_t ** 0.5, a_prev ** 0.5
+            sigma, sigma_prev = (1 - a_t) ** 0.5, (1 - a_prev) ** 0.5
+            if attn_invert:
+                self.attn_state.set_timestep(t)
+            eps = self._eps(latent, t, cond, scale, uncond if scale != 1.0 else None)
+            # latent' = mu * (latent - sigma_prev * eps) / mu_prev + sigma * eps
+            latent = ops.nchw_view(ops.axpby(ops.nhwc(latent), ops.nhwc(eps), float(mu / mu_prev),
+                                             float(sigma - mu * sigma_prev / mu_prev)))
+        return latent
+
+    def _embed(self, text, embeds, what: str) -> torch.Tensor:
+        if embeds is None:
+            if self.encode_prompt_fn is None or text is None:
+                raise ValueError(f"{what}: the CLIP text encoder is outside this build - pass the embedding tensor "
+                                 f"[1, 77, {self.unet.config.cross_attention_dim}] or construct the pipeline with encode_prompt=")
+            embeds = self.encode_prompt_fn(text)
+        return embeds.to(device=self.device, dtype=torch.float32).reshape(1, -1, self.unet.config.cross_attention_dim)
+
+    # ------------------------------------------------------------------ the call
+    @torch.no_grad()
+    def __call__(self, images: Sequence, prompt: Optional[str] = None, num_inference_steps: int = 50,
+                 guidance_scale: float = 7.5, strength: float = -1, negative_prompt: Optional[str] = None,
+                 generator=None, latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None, inv_prompt: str = "",
+                 inv_prompt_embeds: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, use_sdedit: bool = False, frame_batch: Optional[int] = None, **kwargs):
+        if use_sdedit:
+            raise NotImplementedError("use_sdedit: the inversion-based initialisation is the path the reference's script uses")
+        dev = self.device
+        num_frames = len(images)
+        do_cfg = guidance_scale > 1.0
+        pos = self._embed(prompt, prompt_embeds, "prompt")
+        neg = self._embed(negative_prompt if negative_prompt is not None else "", negative_prompt_embeds, "negative prompt") \
+            if do_cfg else None
+        inv = self._embed(inv_prompt, inv_prompt_embeds, "inversion prompt")
+
+        # cross-frame processors on every attention (:503-512); cross-attention calls pass through them (:126-128)
+        ori = self.unet.attn_processors
+        st = self.attn_state = AttnState()
+        self.unet.set_attn_processor({k: CrossFrameAttnProcessor(st) for k in ori})
+        try:
+            self.scheduler.set_timesteps(num_inference_steps)
+            timesteps = self.scheduler.timesteps
+            if strength >= 0:
+                timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength)
+            ts = [int(t) for t in timesteps]
+
+            # 5. per-frame DDIM inversion, frame 0 stores its attention inputs, the others load them (:591-607)
+            st.reset()
+            lat0 = self.ddim_inversion(self.image2latent(images[0]), ts, inv, 1.0, attn_invert=True)
+            st.to_load()
+            fb = frame_batch or num_frames
+            rest = [self.image2latent(images[i]) for i in range(1, num_frames)]
+            inverted = [lat0]
+            for lo in range(0, len(rest), fb):
+                chunk = torch.cat(rest[lo:lo + fb], dim=0)
+                inverted.append(self.ddim_inversion(chunk, ts, inv, 1.0, attn_invert=True))
+            lat = torch.cat(inverted, dim=0).contiguous()
+            if latents is not None:                 # the reference lets caller-supplied start latents through (:579-589)
+                lat = latents.to(device=dev, dtype=torch.float32)
+
+            # 6. reverse pass of frame 0 in STORE state: records the maps the other frames attend to (:612-649)
+            st.reset()
+            st.set_store_id(0)
+            x = lat[:1]
+            for t in ts:
+                st.set_timestep(t)
+                eps = self._eps(x, t, pos, guidance_scale, neg)
+                x = self.scheduler.step(eps, t, x).prev_sample
+
+            # 7. denoising loop: every frame in LOAD state (:657-697)
+            st.to_load()
+            for t in ts:
+                st.set_timestep(t)
+                eps_parts = [self._eps(lat[lo:lo + fb], t, pos, guidance_scale, neg) for lo in range(0, num_frames, fb)]
+                eps = eps_parts[0] if len(eps_parts) == 1 else torch.cat([e.contiguous() for e in eps_parts], dim=0)
+                lat = self.scheduler.step(eps, t, lat).prev_sample
+        finally:
+            self.unet.set_attn_processor(ori)       # :743
+
+        if output_type == "latent":
+            image = lat
+        else:
+            sf = self.vae.config.scaling_factor
+            image = torch.cat([self.vae.decode(lat[i:i + 1] / sf).sample for i in range(num_frames)], dim=0)   # :721-727
+            if output_type != "pt":
+                image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
+                if output_type == "pil":
+                    from PIL import Image
+                    image = [Image.fromarray((im * 255).round().astype("uint8")) for im in image]
+        return StableDiffusionPipelineOutput(images=image) if return_dict else (image, None)

@@ -668,6 +668,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the eps-vs-oracle check of the benchmarked class")
     ap.add_argument("--dump-breakdown", default=None, help="write the per-shape kernel timing table (CSV) here")
     ap.add_argument("--no-vae", action="store_true", help="skip the alias-free VAE decode side measurement (config #3)")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="profiling aid (ncu launch lists): only the device-resident timed region, then exit")
     ap.add_argument("--vae-batch", type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -764,6 +766,13 @@ def main():
     ms_max = allmax(ev0.elapsed_time(ev1))
     value = args.steps / (ms_max / 1000.0)
     finite = bool(torch.isfinite(gd.x).all().item())
+    if args.timed_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_max / args.steps, "note": "--timed-only (profiling aid)"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public call: pinned host latents in, pinned host latents out, every step
     h_in = shard.clone().pin_memory()

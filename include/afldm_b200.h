@@ -250,6 +250,11 @@ AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, 
 AFLDM_API int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
                                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
 
+/* diffusers GEGLU, the feed-forward gate of BasicTransformerBlock in the SD-1.5 UNet2DConditionModel that
+ * afldm/pipelines/video_equiv_editing_pipeline.py:680-686 evaluates: proj [rows][2H] -> y [rows][H],
+ * y = proj[:, :H] * gelu(proj[:, H:]) with the exact (erf) GELU.  H % 4 == 0, 16-byte aligned pointers. */
+AFLDM_API int afldm_geglu_f32(const float* proj, float* y, long long rows, int H, afldm_stream_t stream);
+
 /* ---- cross-frame attention map store (afldm/pipelines/cross_frame_attn.py:78-97) -------------
  * CrossFrameAttnProcessor keeps, per attention layer, the layer input of the reference frame for every timestep
  * (`self.maps[store_id][t] = hidden_states`, keyed by the HOST value t.item() :31-33) and feeds it back as the K / V source

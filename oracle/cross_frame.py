@@ -36,10 +36,13 @@ class AttnState:
 
 
 class CrossFrameAttnProcessor(AttnProcessor2_0):
-    def __init__(self, attn_state: AttnState, enable_interp=False):
+    def __init__(self, attn_state: AttnState, enable_interp=False, base=None):
+        """``base``: the plain processor this one extends (default: the 4-D attention-block form of oracle.nn; pass
+        ``oracle.nn_cond.AttnProcessor2_0()`` for the 3-D transformer form of the SD-1.5 UNet)."""
         self.attn_state = attn_state
         self.maps = [dict(), dict()]
         self.enable_interp = enable_interp
+        self.base = base
 
     def _kv_source(self, attn, m, batch):
         # cross_frame_attn.py:79-97: (n,c,h,w) -> (n,hw,c), group-norm it, tile over the batch
@@ -55,7 +58,7 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
         st = self.attn_state
-        base = super().__call__
+        base = super().__call__ if self.base is None else self.base
         if encoder_hidden_states is not None or st.state == AttnState.IDLE:
             return base(attn, hidden_states, encoder_hidden_states, attention_mask, temb)
         t = st.timestep
