@@ -176,8 +176,9 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, one MUFU; -i
 // two MMAs; ncu on the MT = 1 version showed ~700 issued instructions per 48 HMMA, profiles/r01_ncu_attention.md),
 // 1 for short ones (more CTAs).  K fragments are read as 64-bit words: MMA k-index t <- head-dim column 2t,
 // t + 4 <- 2t + 1 inside each 8-column chunk, the Q fragment uses the same permutation.
+// Head dims above 64 (SD-1.5: 80 and 160) keep Q and O fragments of D / 8 k-steps in registers: one or two CTAs per SM.
 template <int D, int MT>
-__global__ void __launch_bounds__(128, MT == 2 ? 3 : 5)
+__global__ void __launch_bounds__(128, D > 96 ? 1 : (D > 64 ? 2 : (MT == 2 ? 3 : 5)))
 attention_mma_kernel(const float* __restrict__ q, int q_pitch, const float* __restrict__ k,
                      const float* __restrict__ v, int kv_pitch, float* __restrict__ o, int o_pitch,
                      int Bkv_rep, int Nq, int Nk, float qscale) {
@@ -379,12 +380,10 @@ int launch_mma_mt(const float* q, int q_pitch, const float* k, const float* v, i
     const float qscale = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
     constexpr int PK = (D % 32 == 8) ? D : ((D / 32) * 32 + 40);
     constexpr int smem = 2 * 64 * (PK + D + 4) * 4;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
+    if (smem > 48 * 1024) {         // per (function, device): set on every launch (a host-side no-op after the first)
         cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    configured = true;
     launch_k(attention_mma_kernel<D, MT>, dim3(ceil_div(Nq, 64 * MT), heads, B), dim3(128), smem, st,
         q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, qscale);
     return launched();
@@ -396,8 +395,10 @@ int launch_mma(const float* q, int q_pitch, const float* k, const float* v, int 
     // two query tiles per warp once there are enough CTAs left to fill the chip twice over
     static const int force_mt = getenv("AFLDM_ATTN_MT") ? atoi(getenv("AFLDM_ATTN_MT")) : 0;
     if (force_mt == 1) return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
-    if (D <= 32 && Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
-        return launch_mma_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    if constexpr (D <= 32) {
+        if (Nq >= 256 && (long long)ceil_div(Nq, 128) * heads * B >= 2 * 148)
+            return launch_mma_mt<D, 2>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
+    }
     return launch_mma_mt<D, 1>(q, q_pitch, k, v, kv_pitch, o, o_pitch, B, Bkv, Nq, Nk, heads, st);
 }
 
@@ -737,6 +738,8 @@ extern "C" int afldm_attention_f32(const float* q, int q_pitch, const float* k, 
             AFLDM_ATT_MMA(40)
             AFLDM_ATT_MMA(48)
             AFLDM_ATT_MMA(64)
+            AFLDM_ATT_MMA(80)
+            AFLDM_ATT_MMA(160)
             default: return AFLDM_E_NOKERNEL;
         }
 #undef AFLDM_ATT_MMA

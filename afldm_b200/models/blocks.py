@@ -138,10 +138,12 @@ class AttnProcessor2_0:
         if attn.to_q.weight.shape[0] != c:
             raise NotImplementedError("attention with inner_dim != query_dim")
         d = c // attn.heads
-        fast = d <= 64 and d % 8 == 0          # head dims the flash kernels cover (24 in the LDM UNet, 40 in SD-1.5)
+        # head dims the flash kernels cover: up to 64 in both classes (24 in the LDM UNet, 40 in SD-1.5), 80 / 160 (SD-1.5's
+        # deeper levels) on the TF32 tensor-core kernel; the exact-fp32 class runs those as GEMM + row softmax + GEMM
+        fast = d % 8 == 0 and (d <= 64 or (d in (80, 160) and ops.default_conv_algo() == "tf32"))
         # TF32 class: the projections may hand q | k | v over as fp16 (same 11-bit significands as TF32 operands)
         # to the ldmatrix / mma.m16n8k16 attention kernel
-        f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and fast
+        f16 = ops.F16_ATTENTION and ops.default_conv_algo() == "tf32" and fast and d <= 64
         # ... and then the normalised input and the attention output, each consumed by ONE projection, are stored as
         # fp16 too (kind::f16 projections: half the operand bytes)
         half = (f16 and encoder_hidden_states is None and attn.group_norm is not None

@@ -134,6 +134,67 @@ class VideoEquivariantEditingPipeline:
             embeds = self.encode_prompt_fn(text)
         return embeds.to(device=self.device, dtype=torch.float32).reshape(1, -1, self.unet.config.cross_attention_dim)
 
+    @torch.no_grad()
+    def edit_latents(self, frame_latents: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], inv: torch.Tensor,
+                     num_inference_steps: int = 50, strength: float = -1, guidance_scale: float = 7.5,
+                     frame_batch: Optional[int] = None, start_latents: Optional[torch.Tensor] = None,
+                     reference_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The latent-space part of ``__call__`` (:503-697) on VAE-encoded frames [F,4,h,w]: cross-frame processors,
+        per-frame inversion, STORE pass of the reference frame, LOAD denoising of every frame.
+
+        ``reference_latent`` [1,4,h,w]: the frame whose attention maps everybody attends to (default: frame 0 of
+        ``frame_latents``).  A rank that holds only a SLICE of the video passes the encoded frame 0 here and re-runs its
+        inversion + STORE pass locally - ~1/F of the work - instead of receiving the maps of 2 x 16 attention layers x
+        steps from rank 0."""
+        dev = self.device
+        frame_latents = frame_latents.to(device=dev, dtype=torch.float32)
+        num_frames = frame_latents.shape[0]
+        own_reference = reference_latent is None
+        ref0 = frame_latents[:1] if own_reference else reference_latent.to(device=dev, dtype=torch.float32)
+        # cross-frame processors on every attention (:503-512); cross-attention calls pass through them (:126-128)
+        ori = self.unet.attn_processors
+        st = self.attn_state = AttnState()
+        self.unet.set_attn_processor({k: CrossFrameAttnProcessor(st) for k in ori})
+        try:
+            self.scheduler.set_timesteps(num_inference_steps)
+            timesteps = self.scheduler.timesteps
+            if strength >= 0:
+                timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength)
+            ts = [int(t) for t in timesteps]
+
+            # 5. per-frame DDIM inversion, the reference frame stores its attention inputs, the others load them (:591-607)
+            st.reset()
+            lat0 = self.ddim_inversion(ref0, ts, inv, 1.0, attn_invert=True)
+            st.to_load()
+            fb = frame_batch or num_frames
+            rest = frame_latents[1:] if own_reference else frame_latents
+            inverted = [lat0] if own_reference else []
+            for lo in range(0, rest.shape[0], fb):
+                inverted.append(self.ddim_inversion(rest[lo:lo + fb].contiguous(), ts, inv, 1.0, attn_invert=True))
+            lat = torch.cat(inverted, dim=0).contiguous()
+            if start_latents is not None:           # the reference lets caller-supplied start latents through (:579-589)
+                lat = start_latents.to(device=dev, dtype=torch.float32)
+
+            # 6. reverse pass of the reference frame in STORE state: records the maps the other frames attend to (:612-649)
+            st.reset()
+            st.set_store_id(0)
+            x = lat[:1] if own_reference else lat0
+            for t in ts:
+                st.set_timestep(t)
+                eps = self._eps(x, t, pos, guidance_scale, neg)
+                x = self.scheduler.step(eps, t, x).prev_sample
+
+            # 7. denoising loop: every frame in LOAD state (:657-697)
+            st.to_load()
+            for t in ts:
+                st.set_timestep(t)
+                eps_parts = [self._eps(lat[lo:lo + fb], t, pos, guidance_scale, neg) for lo in range(0, num_frames, fb)]
+                eps = eps_parts[0] if len(eps_parts) == 1 else torch.cat([e.contiguous() for e in eps_parts], dim=0)
+                lat = self.scheduler.step(eps, t, lat).prev_sample
+        finally:
+            self.unet.set_attn_processor(ori)       # :743
+        return ops.to_nchw_contiguous(ops.nhwc(lat))
+
     # ------------------------------------------------------------------ the call
     @torch.no_grad()
     def __call__(self, images: Sequence, prompt: Optional[str] = None, num_inference_steps: int = 50,
@@ -152,49 +213,9 @@ class VideoEquivariantEditingPipeline:
             if do_cfg else None
         inv = self._embed(inv_prompt, inv_prompt_embeds, "inversion prompt")
 
-        # cross-frame processors on every attention (:503-512); cross-attention calls pass through them (:126-128)
-        ori = self.unet.attn_processors
-        st = self.attn_state = AttnState()
-        self.unet.set_attn_processor({k: CrossFrameAttnProcessor(st) for k in ori})
-        try:
-            self.scheduler.set_timesteps(num_inference_steps)
-            timesteps = self.scheduler.timesteps
-            if strength >= 0:
-                timesteps, num_inference_steps = self.get_timesteps(num_inference_steps, strength)
-            ts = [int(t) for t in timesteps]
-
-            # 5. per-frame DDIM inversion, frame 0 stores its attention inputs, the others load them (:591-607)
-            st.reset()
-            lat0 = self.ddim_inversion(self.image2latent(images[0]), ts, inv, 1.0, attn_invert=True)
-            st.to_load()
-            fb = frame_batch or num_frames
-            rest = [self.image2latent(images[i]) for i in range(1, num_frames)]
-            inverted = [lat0]
-            for lo in range(0, len(rest), fb):
-                chunk = torch.cat(rest[lo:lo + fb], dim=0)
-                inverted.append(self.ddim_inversion(chunk, ts, inv, 1.0, attn_invert=True))
-            lat = torch.cat(inverted, dim=0).contiguous()
-            if latents is not None:                 # the reference lets caller-supplied start latents through (:579-589)
-                lat = latents.to(device=dev, dtype=torch.float32)
-
-            # 6. reverse pass of frame 0 in STORE state: records the maps the other frames attend to (:612-649)
-            st.reset()
-            st.set_store_id(0)
-            x = lat[:1]
-            for t in ts:
-                st.set_timestep(t)
-                eps = self._eps(x, t, pos, guidance_scale, neg)
-                x = self.scheduler.step(eps, t, x).prev_sample
-
-            # 7. denoising loop: every frame in LOAD state (:657-697)
-            st.to_load()
-            for t in ts:
-                st.set_timestep(t)
-                eps_parts = [self._eps(lat[lo:lo + fb], t, pos, guidance_scale, neg) for lo in range(0, num_frames, fb)]
-                eps = eps_parts[0] if len(eps_parts) == 1 else torch.cat([e.contiguous() for e in eps_parts], dim=0)
-                lat = self.scheduler.step(eps, t, lat).prev_sample
-        finally:
-            self.unet.set_attn_processor(ori)       # :743
+        frame_latents = torch.cat([self.image2latent(img) for img in images], dim=0)
+        lat = self.edit_latents(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
+                                frame_batch=frame_batch, start_latents=latents)
 
         if output_type == "latent":
             image = lat
