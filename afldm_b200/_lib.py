@@ -66,6 +66,7 @@ SIGNATURES = {
     "afldm_axpby_dev_f32": (_i, [_p, _p, _p, _p, _ll, _p]),
     "afldm_slot_copy_f32": (_i, [_p, _p, _ll, _p, _i, _p]),
     "afldm_geglu_f32": (_i, [_p, _p, _ll, _i, _p]),
+    "afldm_act_bwd_mul_f32": (_i, [_p, _p, _p, _ll, _i, _p]),
     "afldm_plane_sep_transform_workspace_floats": (_sz, [_i, _i, _i]),
     "afldm_plane_sep_transform_f32": (_i, [_p, _p, _p, _p, _p, _sz, _i, _i, _i, _i, _i, _i, _p]),
     "afldm_upfirdn2d_f32": (_i, [_p, _p, _p] + [_i] * 15 + [_f, _p]),

@@ -139,6 +139,9 @@ class UpsampleRFFT(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n = _square(x, "UpsampleRFFT")
         if self.up == 2 and self.factor == 1.0 and _fused_ok(n, x.shape[1]):
+            if torch.is_grad_enabled() and x.requires_grad:
+                from ..af_modules.autograd import up2_ideal
+                return up2_ideal(x)
             return ops.nchw_view(ops.up2_ideal(ops.nhwc(x)))
         if self.up == 1 and self.factor == 1.0:
             return self.recon_filter(x)
@@ -152,6 +155,9 @@ class LPFDown2(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         n2 = _square(x, "LPFDown2")
         if n2 % 2 == 0 and _fused_ok(n2 // 2, x.shape[1]):
+            if torch.is_grad_enabled() and x.requires_grad:
+                from ..af_modules.autograd import lpf_down2
+                return lpf_down2(x)
             return ops.nchw_view(ops.lpf_down2(ops.nhwc(x)))
         d = filter_matrix(n2, 0.5, 0.0)[::2, :]
         return sep_transform(x, d, d)

@@ -37,6 +37,9 @@ class WarpedNonlinearity(nn.Module):
             if flat.shape[-1] % 4 == 0 and x.is_contiguous():
                 return ops.affine_act(flat, None, None, self.act).view(x.shape)
             return self.nonlinearity(x)
+        if torch.is_grad_enabled() and x.requires_grad:            # differentiable form
+            from .autograd import filtered_act
+            return filtered_act(x, self.act)
         return ops.nchw_view(ops.filtered_act(ops.nhwc(x), act=self.act))
 
 

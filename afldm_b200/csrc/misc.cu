@@ -240,6 +240,25 @@ geglu_kernel(const float* __restrict__ p, float* __restrict__ y, long long rows,
     }
 }
 
+// ------------------------------------------------------------------ activation derivative (backward of the filtered activation)
+// out = g * act'(z): the elementwise factor between the two linear halves of d/dx [D act(U x U^T) D^T]
+// (training-side use: afldm/trainers/ldm_trainer.py:240-272).  silu'(z) = s (1 + z (1 - s)), s = sigmoid(z).
+__global__ void __launch_bounds__(256)
+act_bwd_mul_kernel(const float* __restrict__ z, const float* __restrict__ g, float* __restrict__ out, long long n, int act) {
+    pdl_trigger();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float d = 1.f;
+        if (act == AFLDM_ACT_SILU) {
+            const float zz = z[i];
+            const float sg = 1.0f / (1.0f + __expf(-zz));
+            d = sg * fmaf(zz, 1.0f - sg, 1.0f);
+        }
+        out[i] = g[i] * d;
+    }
+}
+
 // ------------------------------------------------------------------ slot copy (cross-frame attention maps)
 // table[slot][n] <-> buf[n] with the slot index read from DEVICE memory: a captured denoising step can keep one map per
 // timestep (CrossFrameAttnProcessor, afldm/pipelines/cross_frame_attn.py:78-97, keys its dictionaries by the host value
@@ -453,6 +472,13 @@ extern "C" int afldm_axpby_dev_f32(const float* x, const float* eps, float* out,
                                    long long n, afldm_stream_t stream) {
     if (x == nullptr || eps == nullptr || out == nullptr || coef == nullptr || n <= 0) return AFLDM_E_ARG;
     launch_k(axpby_dev_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, eps, out, coef, n);
+    return launched();
+}
+
+extern "C" int afldm_act_bwd_mul_f32(const float* z, const float* g, float* out, long long n, int act, afldm_stream_t stream) {
+    if (z == nullptr || g == nullptr || out == nullptr || n <= 0) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
+    launch_k(act_bwd_mul_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), z, g, out, n, act);
     return launched();
 }
 

@@ -250,6 +250,11 @@ AFLDM_API int afldm_conv2d_f16in_f32(const void* x, int x_pitch, const void* w, 
 AFLDM_API int afldm_conv2d_f16in_f16out(const void* x, int x_pitch, const void* w, const float* bias, void* y, int y_pitch,
                                         int B, int H, int W, int Cin, int Cout, int ksize, afldm_stream_t stream);
 
+/* Backward of the filtered activation, elementwise part (the reference differentiates through
+ * torch.fft in afldm/trainers/ldm_trainer.py:240-272): out[i] = g[i] * act'(z[i]) on the up-sampled plane, between the two
+ * linear halves U^T (.) U and D^T (.) D, which run as afldm_plane_sep_transform_f32 with the transposed operators. */
+AFLDM_API int afldm_act_bwd_mul_f32(const float* z, const float* g, float* out, long long n, int act, afldm_stream_t stream);
+
 /* diffusers GEGLU, the feed-forward gate of BasicTransformerBlock in the SD-1.5 UNet2DConditionModel that
  * afldm/pipelines/video_equiv_editing_pipeline.py:680-686 evaluates: proj [rows][2H] -> y [rows][H],
  * y = proj[:, :H] * gelu(proj[:, H:]) with the exact (erf) GELU.  H % 4 == 0, 16-byte aligned pointers. */

@@ -149,3 +149,28 @@ def test_base_resamplers_match_oracle():
     x = torch.randn(2, 64, 8, 8, device=DEV)
     with torch.no_grad():
         torch.testing.assert_close(mine(x).contiguous(), ref(x), rtol=0, atol=5e-5)
+
+
+@pytest.mark.parametrize("n,c", [(8, 32), (16, 64), (32, 32)])
+def test_backward_of_resamplers_and_filtered_activation(n, c):
+    """gradients of WarpedNonlinearity / UpsampleRFFT(2) / LPF + decimate through the sm_100a kernels against
+    PyTorch autograd through the oracle's FFT form (what the reference differentiates, ldm_trainer.py:240-272)."""
+    from afldm.af_modules.af_blocks import WarpedNonlinearity
+    from afldm.af_libs.ideal_lpf import UpsampleRFFT
+    from afldm_b200.af_libs.ideal_lpf import LPFDown2
+    gen = torch.Generator().manual_seed(n)
+    x0 = torch.randn(2, c, n, n, generator=gen).to(DEV)
+    cases = [(WarpedNonlinearity(torch.nn.SiLU()), OL.filtered_act_fft, (2, c, n, n)),
+             (UpsampleRFFT(2), lambda t: OL.upsample_rfft(t, 2), (2, c, 2 * n, 2 * n)),
+             (LPFDown2(), lambda t: OL.lpf_rfft(t, 0.5)[:, :, ::2, ::2], None)]
+    for mod, ref, oshape in cases:
+        xin = x0 if oshape is not None else torch.randn(2, c, 2 * n, 2 * n, generator=gen).to(DEV)
+        w = torch.randn(ref(xin).shape, generator=gen).to(DEV)
+        xa = xin.clone().requires_grad_(True)
+        ya = mod(xa)
+        (ya * w).sum().backward()
+        xb = xin.clone().requires_grad_(True)
+        yb = ref(xb)
+        (yb * w).sum().backward()
+        torch.testing.assert_close(ya.detach().contiguous(), yb.detach(), rtol=0, atol=2e-5)
+        torch.testing.assert_close(xa.grad, xb.grad, rtol=0, atol=5e-5)
