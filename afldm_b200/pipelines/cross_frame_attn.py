@@ -78,17 +78,22 @@ class CrossFrameAttnProcessor(AttnProcessor2_0):
         self.enable_interp = enable_interp
         self._tables = [None, None]        # slot mode: [num_slots, n, H, W, C] per store_id
         self._stage = [None, None]         # slot mode: the map of the current step, copied out of the table
+        self._pairs = [{}, {}]             # slot mode: every (table, stage) ever allocated, by shape (graphs point at them)
 
     def _slot_store(self, store_id: int, x_nhwc: torch.Tensor) -> None:
+        """One (table, stage) pair per stored-map SHAPE: a captured step keeps addressing the pair it was captured with
+        when a later STORE pass has another batch (the inversion pass stores 1 map, the guided pass 2)."""
         ctx = self.attn_state.slots
-        tab = self._tables[store_id]
-        if tab is None or tab.shape[1:] != x_nhwc.shape or tab.shape[0] != ctx.num_slots or tab.device != x_nhwc.device:
+        key = (ctx.num_slots, tuple(x_nhwc.shape), str(x_nhwc.device))
+        pair = self._pairs[store_id].get(key)
+        if pair is None:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("cross-frame map table would be allocated during CUDA-graph capture: warm up first")
-            tab = self._tables[store_id] = torch.empty((ctx.num_slots,) + tuple(x_nhwc.shape), dtype=torch.float32,
-                                                       device=x_nhwc.device)
-            self._stage[store_id] = torch.empty(tuple(x_nhwc.shape), dtype=torch.float32, device=x_nhwc.device)
-        ops.slot_copy(tab, x_nhwc.contiguous(), ctx.slot, store=True)
+            pair = self._pairs[store_id][key] = (
+                torch.empty((ctx.num_slots,) + tuple(x_nhwc.shape), dtype=torch.float32, device=x_nhwc.device),
+                torch.empty(tuple(x_nhwc.shape), dtype=torch.float32, device=x_nhwc.device))
+        self._tables[store_id], self._stage[store_id] = pair          # what the next LOAD pass reads
+        ops.slot_copy(pair[0], x_nhwc.contiguous(), ctx.slot, store=True)
 
     def _slot_load(self, store_id: int) -> torch.Tensor:
         tab, stage = self._tables[store_id], self._stage[store_id]

@@ -50,12 +50,67 @@ def _to_tensor(img) -> torch.Tensor:
     return 2.0 * t - 1.0
 
 
+class _CapturedStep:
+    """One step  x <- cx x + ce eps(x, t)  of the video loops as a CUDA graph, eps with or without classifier-free
+    guidance; t, (cx, ce) and the cross-frame slot index live in device memory (cf. ``ldm_pipeline.GraphedDenoiser``).
+    The cross-frame processors must be in slot mode (``AttnState.enable_slots``) and in the state (STORE / LOAD) the
+    captured step is going to be replayed in."""
+
+    def __init__(self, unet, frames: int, size: int, cond: torch.Tensor, uncond: Optional[torch.Tensor], guidance: float,
+                 warmup: int = 2):
+        dev = unet.device
+        c = unet.config.in_channels
+        self.unet, self.frames, self.guidance = unet, frames, float(guidance)
+        self.x = torch.zeros((frames, size, size, c), dtype=torch.float32, device=dev)            # NHWC, updated in place
+        nb = frames * (2 if uncond is not None else 1)
+        self.t = torch.ones((nb,), dtype=torch.float32, device=dev)
+        self.coef = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
+        self.x2 = torch.zeros((nb, size, size, c), dtype=torch.float32, device=dev) if uncond is not None else None
+        parts = ([uncond.expand(frames, -1, -1)] if uncond is not None else []) + [cond.expand(frames, -1, -1)]
+        self.ehs = torch.cat(parts, dim=0).to(device=dev, dtype=torch.float32).contiguous()   # resident before capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.x.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops._lib.launch_count()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self._body()
+        self.launches_per_step = ops._lib.launch_count() - n0
+
+    def set_conditions(self, cond: torch.Tensor, uncond: Optional[torch.Tensor]) -> None:
+        """Refresh the text conditions of a step captured earlier (same shapes)."""
+        f = self.frames
+        if self.x2 is not None:
+            self.ehs[:f].copy_(uncond.expand(f, -1, -1))
+            self.ehs[f:].copy_(cond.expand(f, -1, -1))
+        else:
+            self.ehs.copy_(cond.expand(f, -1, -1))
+
+    def _body(self):
+        f = self.frames
+        if self.x2 is None:
+            eps = ops.nhwc(self.unet(ops.nchw_view(self.x), self.t, encoder_hidden_states=self.ehs, return_dict=False)[0])
+        else:
+            ops.axpby(self.x, self.x, 1.0, 0.0, out=self.x2[:f])          # [uncond x F | cond x F] input
+            ops.axpby(self.x, self.x, 1.0, 0.0, out=self.x2[f:])
+            e = ops.nhwc(self.unet(ops.nchw_view(self.x2), self.t, encoder_hidden_states=self.ehs, return_dict=False)[0])
+            eps = ops.axpby(e[:f], e[f:], 1.0 - self.guidance, self.guidance)
+        ops.axpby(self.x, eps, self.coef, None, out=self.x)
+
+
 class VideoEquivariantEditingPipeline:
     def __init__(self, vae: AutoencoderKL, unet: UNet2DConditionModel, scheduler: DDIMScheduler,
                  encode_prompt: Optional[Callable[[str], torch.Tensor]] = None):
         self.vae, self.unet, self.scheduler = vae, unet, scheduler
         self.encode_prompt_fn = encode_prompt
         self.attn_state = AttnState()
+        self.replayed_launches = 0                # kernels launched through graph replays (the eager counter misses them)
+        self._captured = {}                       # captured steps of the CUDA-graph path, per (steps, size, frames, ...)
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
 
     @classmethod
@@ -138,14 +193,17 @@ class VideoEquivariantEditingPipeline:
     def edit_latents(self, frame_latents: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], inv: torch.Tensor,
                      num_inference_steps: int = 50, strength: float = -1, guidance_scale: float = 7.5,
                      frame_batch: Optional[int] = None, start_latents: Optional[torch.Tensor] = None,
-                     reference_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     reference_latent: Optional[torch.Tensor] = None, use_cuda_graph: bool = False) -> torch.Tensor:
         """The latent-space part of ``__call__`` (:503-697) on VAE-encoded frames [F,4,h,w]: cross-frame processors,
         per-frame inversion, STORE pass of the reference frame, LOAD denoising of every frame.
 
         ``reference_latent`` [1,4,h,w]: the frame whose attention maps everybody attends to (default: frame 0 of
         ``frame_latents``).  A rank that holds only a SLICE of the video passes the encoded frame 0 here and re-runs its
         inversion + STORE pass locally - ~1/F of the work - instead of receiving the maps of 2 x 16 attention layers x
-        steps from rank 0."""
+        steps from rank 0.  ``use_cuda_graph``: replay captured steps (``_edit_latents_captured``)."""
+        if use_cuda_graph and (frame_batch is None or frame_batch >= frame_latents.shape[0]):
+            return self._edit_latents_captured(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
+                                               start_latents, reference_latent)
         dev = self.device
         frame_latents = frame_latents.to(device=dev, dtype=torch.float32)
         num_frames = frame_latents.shape[0]
@@ -195,6 +253,95 @@ class VideoEquivariantEditingPipeline:
             self.unet.set_attn_processor(ori)       # :743
         return ops.to_nchw_contiguous(ops.nhwc(lat))
 
+    @torch.no_grad()
+    def _edit_latents_captured(self, frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
+                               start_latents, reference_latent) -> torch.Tensor:
+        """``edit_latents`` with every UNet evaluation + update replayed from CUDA graphs: the cross-frame maps live in
+        device tables indexed by the step (``AttnState.enable_slots``), timestep / coefficients / slot are device
+        scalars refreshed between replays.  Four captured steps: inversion (reference frame: STORE; other frames: LOAD,
+        no guidance) and denoising (reference frame: STORE; all frames: LOAD, guidance)."""
+        dev = self.device
+        frame_latents = frame_latents.to(device=dev, dtype=torch.float32)
+        num_frames, size = frame_latents.shape[0], frame_latents.shape[-1]
+        own_reference = reference_latent is None
+        ref0 = frame_latents[:1] if own_reference else reference_latent.to(device=dev, dtype=torch.float32)
+        rest = frame_latents[1:] if own_reference else frame_latents
+        sch = self.scheduler
+        sch.set_timesteps(num_inference_steps)
+        timesteps = sch.timesteps
+        if strength >= 0:
+            timesteps, _ = self.get_timesteps(num_inference_steps, strength)
+        ts = [int(t) for t in timesteps]
+        n = len(ts)
+        # coefficient tables: inversion runs over reversed(ts) and writes slot n-1-i (the slot of its timestep)
+        rev = list(reversed(ts))
+        inv_coef = []
+        for i, t in enumerate(rev):
+            a_t = sch.alphas_cumprod[t]
+            a_prev = sch.alphas_cumprod[rev[i - 1]] if i > 0 else sch.final_alpha_cumprod
+            mu, mu_prev = a_t ** 0.5, a_prev ** 0.5
+            sigma, sigma_prev = (1 - a_t) ** 0.5, (1 - a_prev) ** 0.5
+            inv_coef.append([float(mu / mu_prev), float(sigma - mu * sigma_prev / mu_prev)])
+        inv_coef = torch.tensor(inv_coef, dtype=torch.float32, device=dev)
+        den_coef = torch.stack([torch.stack(sch.coefficients(t)) for t in ts]).to(device=dev, dtype=torch.float32)
+        tdev = torch.tensor(ts, dtype=torch.float32, device=dev)
+
+        ori = self.unet.attn_processors
+        do_cfg = neg is not None
+        key = (n, size, num_frames, rest.shape[0], do_cfg, float(guidance_scale), str(dev))
+        cached = self._captured.get(key)
+        if cached is None:
+            st = AttnState()
+            st.enable_slots(n, dev)
+            # the processors own the device tables the captured graphs address: they live as long as the graphs do
+            cached = self._captured[key] = {"state": st, "steps": {},
+                                            "procs": {k: CrossFrameAttnProcessor(st) for k in ori}}
+            while len(self._captured) > 2:                              # graphs pin their activations: keep two shapes
+                self._captured.pop(next(iter(self._captured)))
+        st = self.attn_state = cached["state"]
+        slots = st.slots
+        self.unet.set_attn_processor(cached["procs"])
+
+        def step_for(name, frames, cond, uncond):
+            """The captured step ``name``, built (in the cross-frame state it is first needed in) or refreshed."""
+            stp = cached["steps"].get(name)
+            if stp is None:
+                stp = cached["steps"][name] = _CapturedStep(self.unet, frames, size, cond, uncond, guidance_scale)
+            else:
+                stp.set_conditions(cond.to(dev), None if uncond is None else uncond.to(dev))
+            return stp
+
+        def run(step: _CapturedStep, x0, order, coef):
+            step.x.copy_(ops.nhwc(x0))
+            for i, slot in enumerate(order):
+                step.t.copy_(tdev[slot:slot + 1].expand(step.t.shape[0]))      # device-side broadcast of the timestep
+                step.coef.copy_(coef[i])
+                slots.set_slot(slot)
+                step.graph.replay()
+            self.replayed_launches += step.launches_per_step * len(order)
+            return ops.to_nchw_contiguous(step.x)
+
+        try:
+            inv_order = [n - 1 - i for i in range(n)]
+            st.reset()                                                  # STORE
+            lat0 = run(step_for("inv_store", 1, inv, None), ref0, inv_order, inv_coef)
+            st.to_load()
+            parts = [lat0] if own_reference else []
+            if rest.shape[0] > 0:
+                parts.append(run(step_for("inv_load", rest.shape[0], inv, None), rest, inv_order, inv_coef))
+            lat = torch.cat(parts, dim=0).contiguous()
+            if start_latents is not None:
+                lat = start_latents.to(device=dev, dtype=torch.float32)
+            st.reset()
+            st.set_store_id(0)
+            run(step_for("den_store", 1, pos, neg if do_cfg else None), lat[:1] if own_reference else lat0,
+                list(range(n)), den_coef)
+            st.to_load()
+            lat = run(step_for("den_load", num_frames, pos, neg if do_cfg else None), lat, list(range(n)), den_coef)
+        finally:
+            self.unet.set_attn_processor(ori)
+        return lat
+
     # ------------------------------------------------------------------ the call
     @torch.no_grad()
     def __call__(self, images: Sequence, prompt: Optional[str] = None, num_inference_steps: int = 50,
@@ -202,7 +349,8 @@ class VideoEquivariantEditingPipeline:
                  generator=None, latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
                  negative_prompt_embeds: Optional[torch.Tensor] = None, inv_prompt: str = "",
                  inv_prompt_embeds: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
-                 return_dict: bool = True, use_sdedit: bool = False, frame_batch: Optional[int] = None, **kwargs):
+                 return_dict: bool = True, use_sdedit: bool = False, frame_batch: Optional[int] = None,
+                 use_cuda_graph: bool = False, **kwargs):
         if use_sdedit:
             raise NotImplementedError("use_sdedit: the inversion-based initialisation is the path the reference's script uses")
         dev = self.device
@@ -215,7 +363,7 @@ class VideoEquivariantEditingPipeline:
 
         frame_latents = torch.cat([self.image2latent(img) for img in images], dim=0)
         lat = self.edit_latents(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
-                                frame_batch=frame_batch, start_latents=latents)
+                                frame_batch=frame_batch, start_latents=latents, use_cuda_graph=use_cuda_graph)
 
         if output_type == "latent":
             image = lat

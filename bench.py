@@ -676,7 +676,8 @@ def run_video_workload(args, torch, dev, dist, rank, world):
     ref0 = None if lo == 0 else lat_all[:1].to(dev)
 
     def run():
-        out = pipe.edit_latents(mine, pos, neg, inv, steps, strength, guidance, reference_latent=ref0)
+        out = pipe.edit_latents(mine, pos, neg, inv, steps, strength, guidance, reference_latent=ref0,
+                                use_cuda_graph=not args.video_eager)
         return parallel.gather_frames(out, frames)
 
     def barrier():
@@ -688,27 +689,34 @@ def run_video_workload(args, torch, dev, dist, rank, world):
     barrier()
     n0 = _launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evf = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run()                                          # first call: captures the four steps (eager: a plain warm-up pass)
+    evf.record()
+    barrier()
+    first_ms = ev0.elapsed_time(evf)
+    n0 = _launches() + pipe.replayed_launches
     with ClockSampler(dev.index or 0) as clk:
         ev0.record()
-        out = run()
+        out = run()                                # timed call: same video, captured steps replayed
         ev1.record()
         barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    t = torch.tensor([ev0.elapsed_time(ev1), first_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, first_ms = float(t[0].item()), float(t[1].item())
     used = 35
     if rank == 0:
         line = {"metric": "video_edit_frame_steps_per_sec", "value": frames * used / (ms / 1e3), "unit": "frame-steps/s",
-                "n_gpus": world, "steps": used, "warmup": 1, "ms_per_step": ms / used, "higher_is_better": True,
+                "n_gpus": world, "steps": used, "warmup": 1 * used, "ms_per_step": ms / used, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "TF32 class (see the headline line)", "data": "synthetic",
                 "config": {"workload": f"VideoEquivariantEditingPipeline latent loop, SD-1.5 alias-free UNet2DConditionModel (859.5M params), "
                                        f"{frames} frames x CFG 2 at 64x64x4 latents, 50 DDIM steps at strength 0.7 (35 used): per-frame "
-                                       "inversion + STORE pass of frame 0 + batched LOAD denoising; eager launches",
+                                       "inversion + STORE pass of frame 0 + batched LOAD denoising; " + ("eager launches" if args.video_eager else "captured steps (4 CUDA graphs kept by the pipeline; the timed call replays them, first_call_ms includes capture)"),
                            "global_batch": frames, "per_gpu_frames": hi - lo,
                            "l2": "3.4 GB of weights per UNet evaluation >> 126 MB L2"},
                 "clocks": clk.summary(), "finite": bool(torch.isfinite(out).all().item()), "total_ms": ms,
-                "gpu_launches": _launches() - n0,
+                "first_call_ms": first_ms, "gpu_launches": _launches() + pipe.replayed_launches - n0,
                 "e2e": {"value": frames * used / (ms / 1e3), "unit": "frame-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "the timed call is the public pipeline method on device-resident frame latents; VAE encode / decode at 512x512 is outside the kernels' plane range (<= 128 for the small side)"},
                 "cpu_baseline": None}
@@ -723,6 +731,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d", "shift_ldm", "video"])
     ap.add_argument("--video-frames", type=int, default=16)
+    ap.add_argument("--video-eager", action="store_true", help="config #4 with eager launches instead of captured steps")
     ap.add_argument("--conv-algo", default=os.environ.get("AFLDM_CONV_ALGO", "tf32"), choices=["simt", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")

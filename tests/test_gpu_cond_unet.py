@@ -132,6 +132,24 @@ def test_video_pipeline_matches_oracle_loop():
     one = pipe(frames, prompt_embeds=pos, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
                strength=0.7, guidance_scale=7.5, output_type="latent", frame_batch=1).images
     torch.testing.assert_close(one.contiguous(), lat.contiguous(), rtol=0, atol=1e-4)
+    # the same loops replayed from captured steps (device-indexed cross-frame map tables)
+    cap = pipe(frames, prompt_embeds=pos, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
+               strength=0.7, guidance_scale=7.5, output_type="latent", use_cuda_graph=True).images
+    torch.testing.assert_close(cap.contiguous(), lat.contiguous(), rtol=0, atol=1e-5)
+    # a second call reuses the captured steps with NEW text conditions (refreshed in place) - still the eager result
+    pos2 = pos.flip(1).contiguous()
+    eag2 = pipe(frames, prompt_embeds=pos2, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
+                strength=0.7, guidance_scale=7.5, output_type="latent").images
+    n_cached = len(pipe._captured)
+    cap2 = pipe(frames, prompt_embeds=pos2, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
+                strength=0.7, guidance_scale=7.5, output_type="latent", use_cuda_graph=True).images
+    assert len(pipe._captured) == n_cached and not torch.equal(eag2, lat)
+    # the inversion pass stores 1 map per layer, the guided pass 2: both tables must stay allocated, the captured
+    # steps address them by pointer
+    procs = next(iter(pipe._captured.values()))["procs"]
+    assert all(len(p._pairs[0]) == 2 for p in procs.values() if p._pairs[0])
+    torch.testing.assert_close(cap2.contiguous(), eag2.contiguous(), rtol=0, atol=1e-5)
+    assert mine.attn_processors == before
     with pytest.raises(ValueError):
         pipe(frames, prompt="a red car", num_inference_steps=2)    # no text encoder in this build: embeddings required
 
