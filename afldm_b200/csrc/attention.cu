@@ -672,12 +672,11 @@ int launch_f16_mt(const __half* q, int q_pitch, const __half* k, const __half* v
     const float scale_log2e = (float)((1.0 / sqrt((double)D)) * 1.4426950408889634);
     constexpr int DP = (D + 15) / 16 * 16;
     constexpr int smem = 4 * 64 * (DP + 8) * 2;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(attention_f16_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (smem > 48 * 1024) {
+        static std::atomic<unsigned long long> configured{0};
+        cudaError_t e = set_max_dyn_smem(attention_f16_kernel<D, MT>, smem, configured);
         if (e != cudaSuccess) return (int)e;
     }
-    configured = true;
     launch_k(attention_f16_kernel<D, MT>, dim3(ceil_div(Nq, 64 * MT), heads, B), dim3(128), smem, st,
         q, q_pitch, k, v, kv_pitch, o, o_pitch, B / Bkv, Nq, Nk, scale_log2e, o_half);
     return launched();

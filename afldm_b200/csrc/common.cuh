@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/afldm_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -83,5 +85,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the CURRENT DEVICE's copy of the function, not to the process:
+// one bit per device ordinal records where it has been set (idempotent and thread-safe: two racing threads both set it).
+template <typename K>
+inline cudaError_t set_max_dyn_smem(K kern, int bytes, std::atomic<unsigned long long>& done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 }  // namespace afldm

@@ -1048,8 +1048,10 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
             return AFLDM_E_NOKERNEL;
     }
 
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};      // one bit per device ordinal (the attribute is per device)
+    int dev_ord = 0;
+    if (cudaGetDevice(&dev_ord) != cudaSuccess) return AFLDM_E_NOKERNEL;
+    if (!(configured.load(std::memory_order_acquire) & (1ull << (dev_ord & 63)))) {
         cudaError_t e = cudaSuccess;
         const void* kerns[8] = {(const void*)conv_tc_kernel<false, false, false>, (const void*)conv_tc_kernel<false, true, false>,
                                 (const void*)conv_tc_kernel<true, false, false>, (const void*)conv_tc_kernel<true, true, false>,
@@ -1059,7 +1061,7 @@ int conv_tc_launch(const float* x, int x_pitch, const float* w, const float* bia
             e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ONE_PER_SM + BARRIER_BYTES);
             if (e != cudaSuccess) return (int)e;
         }
-        configured = true;
+        configured.fetch_or(1ull << (dev_ord & 63), std::memory_order_release);
     }
     TcArgs a;
     a.bias = bias; a.row_add = row_add; a.residual = residual; a.y = y; a.ws = workspace;

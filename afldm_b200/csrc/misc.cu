@@ -397,12 +397,10 @@ extern "C" int afldm_linear_rows_f32(const float* x, const float* w, const float
 #define AFLDM_LIN(AI, AO)                                                                              \
     {                                                                                                  \
         if (fast768) {                                                                                 \
-            static bool cfg768 = false;                                                                \
-            if (!cfg768) {                                                                             \
-                cudaError_t e = cudaFuncSetAttribute(linear_rows_k768_kernel<AI, AO>,                  \
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+            static std::atomic<unsigned long long> cfg768{0};                                          \
+            {                                                                                          \
+                cudaError_t e = set_max_dyn_smem(linear_rows_k768_kernel<AI, AO>, 64 * 1024, cfg768);  \
                 if (e != cudaSuccess) return (int)e;                                                   \
-                cfg768 = true;                                                                         \
             }                                                                                          \
             launch_k(linear_rows_k768_kernel<AI, AO>, dim3(blocks768), dim3(256), smem, st, x, w, bias, y, M, N); \
             return launched();                                                                         \

@@ -648,11 +648,10 @@ template <int N, int ACT, int TERMS>
 int launch_fact_mma_t(const float* x, float* y, int B, int C, const Affine& af, cudaStream_t st) {
     auto kern = fact_mma_kernel<N, ACT, TERMS>;
     constexpr int smem = FmTile<N>::SMEM_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::atomic<unsigned long long> configured{0};      // one bit per device
+    {
+        cudaError_t e = set_max_dyn_smem(kern, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     launch_k(kern, dim3(C / FM_CG, B), dim3(FM_THREADS), smem, st, x, y, C, af);
     return launched();
@@ -677,11 +676,10 @@ int launch_one(const float* x, float* y, int B, int C, const Affine& af, cudaStr
     if (C % CG != 0) return AFLDM_E_SHAPE;
     auto kern = (N >= 32) ? resample_phased_kernel<N, CG, MODE, ACT> : resample_kernel<N, CG, MODE, ACT>;
     constexpr int smem = Tile<N, CG>::SMEM_BYTES;
-    static bool configured = false;  // attribute is per-function, set once (idempotent)
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::atomic<unsigned long long> configured{0};      // one bit per device
+    {
+        cudaError_t e = set_max_dyn_smem(kern, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     constexpr int tasks = 2 * N * CG;
     const int threads = tasks >= 256 ? 256 : (tasks < 32 ? 32 : tasks);

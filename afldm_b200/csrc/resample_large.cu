@@ -151,11 +151,10 @@ int launch_lines(const LineArgs& a, cudaStream_t st) {
     constexpr int LEN_A = (OP == OP_DOWN) ? 2 * N : N;
     constexpr int smem = (LEN_A + (OP == OP_UPACTDOWN ? N : 0)) * L * 32 * 4;
     auto kern = line_kernel<N, OP, ACT, L>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::atomic<unsigned long long> configured{0};      // one bit per device
+    {
+        cudaError_t e = set_max_dyn_smem(kern, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     launch_k(kern, dim3(a.C / 32, ceil_div(a.n_lines, L)), dim3(32 * L), smem, st, a);
     return 0;
@@ -442,11 +441,10 @@ template <int N, int OP, int ACT>
 int launch_lines_mma(const LineArgs& a, cudaStream_t st) {
     constexpr int smem = 2 * (N / 8) * 32 * 16 + LM_WARPS * N * LM_EP * 4;
     auto kern = line_mma_kernel<N, OP, ACT>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::atomic<unsigned long long> configured{0};      // one bit per device
+    {
+        cudaError_t e = set_max_dyn_smem(kern, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     launch_k(kern, dim3(a.C / 8, ceil_div(ceil_div(a.n_lines, 2), LM_WARPS)), dim3(32 * LM_WARPS), smem, st, a);
     return 0;
