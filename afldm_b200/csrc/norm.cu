@@ -161,6 +161,28 @@ affine_act_kernel(const float4* __restrict__ x, float4* __restrict__ y, long lon
     }
 }
 
+// The same pass for channel counts that are no multiple of 4 (or unaligned pointers): one element per thread.  Only the
+// general-plane form of the ideal resamplers and odd-channel callers reach it.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+affine_act_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int C, long long per_image,
+                         const float* __restrict__ scale, const float* __restrict__ shift, int y_half) {
+    pdl_trigger();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = x[i];
+        if (scale != nullptr) {
+            const long long b = i / per_image;
+            const int c = (int)(i % C);
+            v = fmaf(v, scale[b * C + c], shift[b * C + c]);
+        }
+        v = apply_act<ACT>(v);
+        if (y_half) reinterpret_cast<__half*>(y)[i] = __float2half_rn(v);
+        else y[i] = v;
+    }
+}
+
 // GroupNorm finalisation + y = act(x * scale + shift) in ONE launch (normalised input of an attention block):
 // every CTA first turns the producer's partial sums of ITS image into per-channel scale / shift in shared memory
 // (one warp per group, fp32 adds, fp64 only for E[x^2] - mean^2; a few KB of L2-resident loads), then streams its
@@ -289,8 +311,18 @@ static int affine_act_impl(const float* x, float* y, int y_half, int B, int HW, 
                            const float* scale, const float* shift, afldm_stream_t stream) {
     if (x == nullptr || y == nullptr || B <= 0 || HW <= 0 || C <= 0) return AFLDM_E_ARG;
     if ((scale == nullptr) != (shift == nullptr)) return AFLDM_E_ARG;
-    if (C % 4 != 0) return AFLDM_E_SHAPE;
-    if (!aligned16(x) || !aligned16(y) || (scale && (!aligned16(scale) || !aligned16(shift)))) return AFLDM_E_ARG;
+    if (act != AFLDM_ACT_SILU && act != AFLDM_ACT_IDENTITY) return AFLDM_E_ARG;
+    if (C % 4 != 0 || !aligned16(x) || !aligned16(y) || (scale && (!aligned16(scale) || !aligned16(shift)))) {
+        const long long n = (long long)B * HW * C;
+        const int blocks1 = (int)min((long long)148 * 8, (n + 255) / 256);
+        if (act == AFLDM_ACT_SILU)
+            launch_k(affine_act_scalar_kernel<AFLDM_ACT_SILU>, dim3(blocks1), dim3(256), 0, as_stream(stream),
+                x, y, n, C, (long long)HW * C, scale, shift, y_half);
+        else
+            launch_k(affine_act_scalar_kernel<AFLDM_ACT_IDENTITY>, dim3(blocks1), dim3(256), 0, as_stream(stream),
+                x, y, n, C, (long long)HW * C, scale, shift, y_half);
+        return launched();
+    }
     const long long n4 = (long long)B * HW * C / 4;
     const long long per_image4 = (long long)HW * C / 4;
     const int blocks = (int)min((long long)148 * 8, (n4 + 255) / 256);

@@ -194,6 +194,38 @@ def to_nchw_contiguous(y: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------- ideal resampling
+GENERAL_PLANES = os.environ.get("AFLDM_GENERAL_PLANES", "1") == "1"
+_UNSUPPORTED = (-1, -3)        # AFLDM_E_SHAPE / AFLDM_E_NOKERNEL: outside the fused kernels' family, nothing launched
+
+
+def _general_resample(x: torch.Tensor, mode: str, act: str = "identity", scale: Optional[torch.Tensor] = None,
+                      shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The three ideal operators for ANY square plane size (n > 128, not a power of two, channel counts outside the
+    fused kernels' groups): the same operator matrices U (2n x n) and D (n x 2n) applied per plane by
+    ``afldm_plane_sep_transform_f32``, with the activation as an ``afldm_affine_act_f32`` pass over the 4x tensor.
+    Like the reference it materialises the up-sampled tensor; unlike the fused kernels it is not a hot-path form
+    (the UNet / VAE configurations of SURVEY.md 8(d) never reach it).  NHWC in, NHWC out."""
+    from .af_libs import ideal_lpf as il
+    b, h, w, c = x.shape
+    if h != w:
+        raise _lib.AfldmError(f"{mode}: square planes expected (the reference builds its mask from the last dimension "
+                              f"only, ideal_lpf.py:81), got {h} x {w}")
+    if scale is not None:                                    # GroupNorm affine: commutes with U (rows of U sum to 1),
+        x = affine_act(x.view(b, h * w, c), scale, shift, "identity").view(b, h, w, c)   # applied first for clarity
+    t = to_nchw_contiguous(x)
+    if mode in ("fact", "up2"):
+        u = il.upsample_matrix(h, 2)
+        t = il.sep_transform(t, u, u)
+    if mode == "fact" and act != "identity":
+        flat = t.view(1, -1, 1024) if t.numel() % 1024 == 0 else t.view(1, -1, 4) if t.numel() % 4 == 0 else t.view(1, -1, 1)
+        affine_act(flat, None, None, act, out=flat)
+    if mode in ("fact", "down2"):
+        n2 = t.shape[-1]
+        d = il.filter_matrix(n2, 0.5, 0.0)[::2, :]
+        t = il.sep_transform(t, d, d)
+    return nhwc(t)
+
+
 def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
                  act: str = "silu", out: Optional[torch.Tensor] = None, out_half: bool = False) -> torch.Tensor:
     """WarpedNonlinearity (af_blocks.py:19-28) on NHWC x, optional folded GroupNorm affine.  ``out_half``: the result
@@ -211,19 +243,26 @@ def filtered_act(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: O
                                                _ptr(scale), _ptr(shift), _ptr(ws), need, _stream())
 
         code = call_h()
-        if code != -3:
+        if code not in _UNSUPPORTED:
             _lib.check(code, "filtered_act_f16out")
             if _recorder is not None:
                 _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h,
                                   (x, outh, scale, shift, ws)))
             return outh
-    if out is None:
-        out = torch.empty_like(x)
-    _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel()),
-         lambda: L.afldm_filtered_act_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act],
-                                          _ptr(scale), _ptr(shift), _ptr(ws), need, _stream()),
-         (x, out, scale, shift, ws))
-    return out
+    dst = torch.empty_like(x) if out is None else out
+
+    def call():
+        return L.afldm_filtered_act_f32(x.data_ptr(), dst.data_ptr(), b, h, w, c, ACT[act],
+                                        _ptr(scale), _ptr(shift), _ptr(ws), need, _stream())
+
+    code = call()
+    if code in _UNSUPPORTED and GENERAL_PLANES and h == w:
+        res = _general_resample(x, "fact", act, scale, shift)
+        return res if out is None else out.copy_(res)
+    _lib.check(code, "filtered_act")
+    if _recorder is not None:
+        _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel()), call, (x, dst, scale, shift, ws)))
+    return dst
 
 
 FUSE_CONCAT = os.environ.get("AFLDM_FUSE_CONCAT", "1") == "1"
@@ -340,18 +379,26 @@ def filtered_act_groupnorm(x: torch.Tensor, groups: int, eps: float, gamma: Opti
                                                           _ptr(gamma), _ptr(beta), _stream())
 
                 code = call_h()
-                if code != -3:
+                if code not in _UNSUPPORTED:
                     _lib.check(code, "filtered_act_gn_f16out")
                     if _recorder is not None:
                         _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), fused_gn=1, f16out=1),
                                           call_h, (x, outh, pa, pb, gamma, beta)))
                     return outh
             out = torch.empty_like(x)
-            _run("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), fused_gn=1),
-                 lambda: L.afldm_filtered_act_gn_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act], pa.data_ptr(),
-                                                     sa, ca, _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma),
-                                                     _ptr(beta), _stream()), (x, out, pa, pb, gamma, beta))
-            return out
+
+            def call():
+                return L.afldm_filtered_act_gn_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, ACT[act], pa.data_ptr(),
+                                                   sa, ca, _ptr(pb), sb, cb, groups, float(eps), _ptr(gamma),
+                                                   _ptr(beta), _stream())
+
+            code = call()
+            if code not in _UNSUPPORTED:          # outside the fused family: statistics + the general-plane form below
+                _lib.check(code, "filtered_act_gn")
+                if _recorder is not None:
+                    _recorder.append(("filtered_act", dict(B=b, N=h, C=c, elems=x.numel(), fused_gn=1), call,
+                                      (x, out, pa, pb, gamma, beta)))
+                return out
     scale, shift = groupnorm_affine(x, groups, eps, gamma, beta)
     return filtered_act(x, scale, shift, act=act, out_half=out_half)
 
@@ -372,7 +419,7 @@ def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
             return Lh.afldm_up2_ideal_f16out(x.data_ptr(), outh.data_ptr(), b, h, w, c, _ptr(wsh), needh, _stream())
 
         code = call_h()
-        if code != -3:
+        if code not in _UNSUPPORTED:
             _lib.check(code, "up2_ideal_f16out")
             if _recorder is not None:
                 _recorder.append(("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel(), f16out=1), call_h, (x, outh, wsh)))
@@ -381,9 +428,17 @@ def up2_ideal(x: torch.Tensor, scale: Optional[torch.Tensor] = None,
     L = _lib.lib()
     need = L.afldm_resample_workspace_floats(1, b, h, w, c)
     ws = scratch(x.device, need) if need else None
-    _run("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel()),
-         lambda: L.afldm_up2_ideal_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, _ptr(scale), _ptr(shift),
-                                       _ptr(ws), need, _stream()), (x, out, scale, shift, ws))
+
+    def call():
+        return L.afldm_up2_ideal_f32(x.data_ptr(), out.data_ptr(), b, h, w, c, _ptr(scale), _ptr(shift),
+                                     _ptr(ws), need, _stream())
+
+    code = call()
+    if code in _UNSUPPORTED and GENERAL_PLANES and h == w:
+        return _general_resample(x, "up2", "identity", scale, shift)
+    _lib.check(code, "up2_ideal")
+    if _recorder is not None:
+        _recorder.append(("up2_ideal", dict(B=b, N=h, C=c, elems=x.numel()), call, (x, out, scale, shift, ws)))
     return out
 
 
@@ -398,16 +453,29 @@ def lpf_down2(x: torch.Tensor, gn_stats: bool = False) -> torch.Tensor:
     L = _lib.lib()
     if gn_stats and h2 // 2 <= 16 and h2 == w2:
         gn = torch.empty((b, 1, c, 2), dtype=torch.float32, device=x.device)
-        _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel(), gn=1),
-             lambda: L.afldm_lpf_down2_gn_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, gn.data_ptr(),
-                                              _stream()), (x, out, gn))
-        out._afldm_gn = (gn, 1, c)
-        return out
+
+        def call_gn():
+            return L.afldm_lpf_down2_gn_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, gn.data_ptr(), _stream())
+
+        code = call_gn()
+        if code not in _UNSUPPORTED:
+            _lib.check(code, "lpf_down2_gn")
+            if _recorder is not None:
+                _recorder.append(("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel(), gn=1), call_gn, (x, out, gn)))
+            out._afldm_gn = (gn, 1, c)
+            return out
     need = L.afldm_resample_workspace_floats(2, b, h2 // 2, w2 // 2, c)
     ws = scratch(x.device, need) if need else None
-    _run("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel()),
-         lambda: L.afldm_lpf_down2_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _ptr(ws), need,
-                                       _stream()), (x, out, ws))
+
+    def call():
+        return L.afldm_lpf_down2_f32(x.data_ptr(), out.data_ptr(), b, h2 // 2, w2 // 2, c, _ptr(ws), need, _stream())
+
+    code = call()
+    if code in _UNSUPPORTED and GENERAL_PLANES and h2 == w2:
+        return _general_resample(x, "down2")
+    _lib.check(code, "lpf_down2")
+    if _recorder is not None:
+        _recorder.append(("lpf_down2", dict(B=b, N=h2 // 2, C=c, elems=x.numel()), call, (x, out, ws)))
     return out
 
 

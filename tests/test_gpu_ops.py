@@ -168,11 +168,17 @@ def test_resampler_linearity_at_full_size():
 
 def test_resampler_rejects_unsupported_shapes():
     with pytest.raises(_lib.AfldmError):
-        ops.filtered_act(torch.zeros(1, 8, 4, 32, device=DEV))          # not square
-    with pytest.raises(_lib.AfldmError):
-        ops.filtered_act(torch.zeros(1, 6, 6, 32, device=DEV))          # no n = 6 specialisation
-    with pytest.raises(_lib.AfldmError):
-        ops.filtered_act(torch.zeros(1, 8, 8, 24, device=DEV))          # C % 32
+        ops.filtered_act(torch.zeros(1, 8, 4, 32, device=DEV))          # not square (neither does the reference: its
+    with pytest.raises(_lib.AfldmError):                                # mask is built from the last dimension only)
+        ops.up2_ideal(torch.zeros(1, 8, 4, 32, device=DEV))
+    # the C ABI itself reports shapes outside the fused kernels' family (nothing launched) ...
+    L = _lib.lib()
+    x6, x24 = torch.zeros(1, 6, 6, 32, device=DEV), torch.zeros(1, 8, 8, 24, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.afldm_filtered_act_f32(x6.data_ptr(), torch.empty_like(x6).data_ptr(), 1, 6, 6, 32, 1, None, None, None, 0, st) == -3
+    assert L.afldm_filtered_act_f32(x24.data_ptr(), torch.empty_like(x24).data_ptr(), 1, 8, 8, 24, 1, None, None, None, 0, st) == -1
+    # ... and the Python op then runs the general-plane form (tests/test_gpu_surface.py::test_general_plane_sizes)
+    assert ops.filtered_act(x6).shape == x6.shape and ops.filtered_act(x24).shape == x24.shape
 
 
 # ----------------------------------------------------------------------------- norm / act

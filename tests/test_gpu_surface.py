@@ -105,6 +105,30 @@ def test_upfirdn2d_python_surface_vs_reference_goldens(golden):
     np.testing.assert_allclose(got.cpu().numpy(), g["gen"], atol=2e-6)
 
 
+@pytest.mark.parametrize("b,c,n", [(2, 24, 12), (1, 8, 20), (2, 5, 6), (1, 3, 48), (1, 4, 256), (2, 24, 8), (1, 7, 32)])
+def test_general_plane_sizes(b, c, n):
+    """Planes outside the fused kernels' family (not a power of two, above 128, channel counts that are no multiple of
+    the kernels' channel groups) run the operator-matrix form (ops._general_resample): same results as the oracle's
+    FFT form, which accepts any square size (ideal_lpf.py:69-93, :148-158; af_blocks.py:19-28)."""
+    gen = torch.Generator().manual_seed(7 * n + c)
+    x = (torch.randn(b, c, n, n, generator=gen) * 1.5).to(DEV)
+    sc = (torch.rand(b, c, generator=gen) + 0.5).to(DEV).contiguous()
+    sh = (torch.randn(b, c, generator=gen) * 0.3).to(DEV).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    tol = 5e-5 if n >= 256 else 1e-5
+    want = OL.filtered_act_fft(x * sc[:, :, None, None] + sh[:, :, None, None])
+    got = ops.filtered_act(xn, sc, sh)
+    assert got.shape == xn.shape and (got.permute(0, 3, 1, 2) - want).abs().max().item() < tol
+    up = ops.up2_ideal(xn)
+    assert (up.permute(0, 3, 1, 2) - OL.upsample_rfft(x)).abs().max().item() < tol
+    dn = ops.lpf_down2(up, gn_stats=True)
+    assert (dn.permute(0, 3, 1, 2) - OL.lpf_rfft(OL.upsample_rfft(x))[..., ::2, ::2]).abs().max().item() < tol
+    # module level: the same call a diffusers block makes
+    from afldm_b200.af_modules.af_blocks import WarpedNonlinearity
+    y = WarpedNonlinearity(torch.nn.SiLU())(x)
+    assert (y - OL.filtered_act_fft(x)).abs().max().item() < tol
+
+
 @pytest.mark.parametrize("b,c,n", [(2, 8, 32), (3, 192, 32), (16, 576, 32), (2, 16, 16), (5, 384, 16)])
 def test_filtered_act_tcgen05_entry_point(b, c, n):
     """afldm_filtered_act_tc: the tcgen05 / TMEM form (csrc/fact_tc.cu) against the oracle's FFT form - the same bounds
