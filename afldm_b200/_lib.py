@@ -109,7 +109,14 @@ def lib() -> C.CDLL:
     return _lib
 
 
+_SYNC_EACH = os.environ.get("AFLDM_SYNC_EACH", "0") == "1"      # debugging aid: wait for every launch (finds the kernel that hangs)
+
+
 def check(code: int, what: str = "") -> None:
+    if _SYNC_EACH and code == 0:
+        import torch
+        if not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize()
     if code != 0:
         msg = lib().afldm_error_string(code).decode()
         raise AfldmError(f"{what or 'afldm call'} failed ({code}): {msg}")

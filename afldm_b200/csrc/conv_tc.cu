@@ -966,6 +966,17 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks, bool f16 = false)
         if (p.stages > MAX_STAGES) { p.csk = 0; p.ok = false; return p; }
     }
     p.smem_bytes = (size_t)p.stages * stage_bytes + (p.alias_staging ? 0 : STAGING_BYTES) + BARRIER_BYTES;
+    // tcgen05.alloc blocks until its columns are free, so TMEM must never be over-subscribed by the conv CTAs that can
+    // share an SM - two CTAs of this launch, the head of a PDL-overlapped successor, a conv_shortcut on the side
+    // stream.  A CTA pair (cta_group::2) that holds its columns on one SM while its peer waits on the other can dead-lock
+    // against a pair of another kernel doing the same (seen on B200: an intermittent hang of the SD-1.5 video loop).
+    // Shared memory is the resource that decides co-residency, so a CTA with c columns asks for enough of it that at
+    // most 512 / c such CTAs fit on an SM (228 KB, 1 KB reserved per CTA).
+    {
+        const int kmax = 512 / p.tmem_cols;
+        const size_t floor_bytes = (size_t)(233472 / (kmax + 1)) - 1024 + 16;
+        if (p.smem_bytes < floor_bytes) p.smem_bytes = floor_bytes;
+    }
     p.ok = true;
     return p;
 }

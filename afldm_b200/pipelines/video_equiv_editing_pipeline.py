@@ -17,12 +17,12 @@ attention kernel reads K/V batch b // F, the same repeat the reference materiali
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Union
+from typing import Callable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, parallel
 from ..models.af_vae import AutoencoderKL
 from ..models.unet_2d_condition import UNet2DConditionModel
 from ..schedulers.ddim import DDIMScheduler
@@ -350,7 +350,11 @@ class VideoEquivariantEditingPipeline:
                  negative_prompt_embeds: Optional[torch.Tensor] = None, inv_prompt: str = "",
                  inv_prompt_embeds: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
                  return_dict: bool = True, use_sdedit: bool = False, frame_batch: Optional[int] = None,
-                 use_cuda_graph: bool = False, **kwargs):
+                 use_cuda_graph: bool = False, shard: Optional[Tuple[int, int]] = None, **kwargs):
+        """:330-748.  ``shard = (rank, world_size)``: this process edits frames ``shard_bounds(len(images), rank, world)``
+        of the video (it encodes frame 0 as well and re-runs its inversion + STORE pass - ``edit_latents``), decodes
+        them, and the call ends with the ONE collective of the path, ``parallel.gather_frames`` of the decoded frames
+        (SURVEY.md 8(e)): every rank returns the whole edited video.  Needs an initialised process group."""
         if use_sdedit:
             raise NotImplementedError("use_sdedit: the inversion-based initialisation is the path the reference's script uses")
         dev = self.device
@@ -361,15 +365,20 @@ class VideoEquivariantEditingPipeline:
             if do_cfg else None
         inv = self._embed(inv_prompt, inv_prompt_embeds, "inversion prompt")
 
-        frame_latents = torch.cat([self.image2latent(img) for img in images], dim=0)
+        lo, hi = (0, num_frames) if shard is None else parallel.shard_bounds(num_frames, int(shard[0]), int(shard[1]))
+        frame_latents = torch.cat([self.image2latent(img) for img in images[lo:hi]], dim=0)
+        reference = None if lo == 0 else self.image2latent(images[0])
         lat = self.edit_latents(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
-                                frame_batch=frame_batch, start_latents=latents, use_cuda_graph=use_cuda_graph)
+                                frame_batch=frame_batch, start_latents=None if latents is None else latents[lo:hi],
+                                reference_latent=reference, use_cuda_graph=use_cuda_graph)
 
         if output_type == "latent":
-            image = lat
+            image = lat if shard is None else parallel.gather_frames(lat.contiguous(), num_frames)
         else:
             sf = self.vae.config.scaling_factor
-            image = torch.cat([self.vae.decode(lat[i:i + 1] / sf).sample for i in range(num_frames)], dim=0)   # :721-727
+            image = torch.cat([self.vae.decode(lat[i:i + 1] / sf).sample for i in range(hi - lo)], dim=0)      # :721-727
+            if shard is not None:
+                image = parallel.gather_frames(image.contiguous(), num_frames)
             if output_type != "pt":
                 image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
                 if output_type == "pil":

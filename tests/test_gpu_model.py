@@ -192,6 +192,31 @@ def test_afvae_decode_and_encode_vs_oracle():
         torch.testing.assert_close(m_got, m_want, rtol=0, atol=2e-4)
 
 
+def test_afvae_decode_512_planes_vs_oracle():
+    """The config #4 image size: 4x64x64 latents -> 3x512x512.  The 256 x 256 filtered activations and the 128 -> 256
+    ideal up-sampler are above the fused kernels' plane range and run the operator-matrix form (ops._general_resample);
+    the encoder's 512 -> 256 down-sampler likewise."""
+    from afldm_b200.models import AliasFreeAutoencoderKL
+    torch.manual_seed(0)
+    ref = ON.AutoencoderKL().to(DEV).eval()
+    jitter(ref, 5)
+    mine = AliasFreeAutoencoderKL.from_config().to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    OA.make_af_vae_from_config(ref)
+    z = randn(1, 4, 64, 64, seed=21)
+    with torch.no_grad():
+        want = ref.decode(z / 0.6).sample
+        got = mine.decode(z / 0.6).sample
+        assert got.shape == (1, 3, 512, 512)
+        err = (got - want).abs().max().item()
+        assert err < 3e-4 * max(1.0, want.abs().max().item()), err
+        img = randn(1, 3, 512, 512, seed=22)
+        m_want = ref.encode(img).latent_dist.mean
+        m_got = mine.encode(img).latent_dist.mean
+        assert m_got.shape == (1, 4, 64, 64)
+        torch.testing.assert_close(m_got, m_want, rtol=0, atol=3e-4)
+
+
 def test_i2sb_bridge_matches_oracle():
     """Config #5 path on a small UNet: the I2SB sampling loop (i2sb_pipeline.py:45-56), ODE mode."""
     from afldm_b200.pipelines import I2SBLDMPipeline
