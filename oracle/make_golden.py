@@ -3,7 +3,8 @@
     PYTHONPATH=/root/reference python oracle/make_golden.py
 
 Imports only reference modules that are importable without diffusers:
-afldm.af_libs.ideal_lpf, afldm.af_libs.torch_utils.ops.upfirdn2d, afldm.shift_utils.{shifters,metrics}.
+afldm.af_libs.ideal_lpf, afldm.af_libs.torch_utils.ops.upfirdn2d, afldm.shift_utils.{shifters,metrics},
+afldm.af_libs.superresolution.
 `/root/reference` cannot travel to the GPU box, so the vectors are committed as small fixtures.
 Test infrastructure only.
 """
@@ -129,6 +130,25 @@ def main():
     sh["mask_psnr"] = RM.mask_psnr(a, b, m).numpy()
     sh["psnr"] = RM.psnr(a, b).numpy()
     np.savez_compressed(os.path.join(OUT, "shift.npz"), **sh)
+
+    # ---- x4 degradation operators of the super-resolution scripts (scripts/shift_ldm_sr.py:45)
+    from afldm.af_libs import superresolution as RSR
+    sr = {}
+    for n in (32, 64):
+        x = torch.rand(2, 3, n, n, generator=torch.Generator().manual_seed(40 + n)) * 2 - 1
+        sr[f"x_{n}"] = x.numpy()
+        for filt in ("bicubic", "pool"):
+            sr[f"sr4x_{filt}_{n}"] = RSR.build_sr4x("cpu", filt, n)(x).numpy()
+        hb = RSR.build_sr_bicubic(4, "cpu", n)
+        y = hb.H(x)
+        sr[f"H_{n}"] = y.numpy()
+        sr[f"Ht_{n}"] = hb.Ht(y).numpy()
+        sr[f"Hpinv_{n}"] = hb.H_pinv(y).numpy()
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(296)) * 2 - 1       # the script's size: checksums
+    y = RSR.build_sr4x("cpu", "bicubic", 256)(x)
+    sr["sum_256"] = np.array([y.double().sum().item(), y.double().abs().sum().item()])
+    sr["rows_256"] = y[0, :, ::37, ::41].numpy()
+    np.savez_compressed(os.path.join(OUT, "superres.npz"), **sr)
 
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

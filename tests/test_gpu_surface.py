@@ -198,3 +198,29 @@ def test_backward_of_resamplers_and_filtered_activation(n, c):
         (yb * w).sum().backward()
         torch.testing.assert_close(ya.detach().contiguous(), yb.detach(), rtol=0, atol=2e-5)
         torch.testing.assert_close(xa.grad, xb.grad, rtol=0, atol=5e-5)
+
+
+def test_superresolution_x4_degradation(golden):
+    """``afldm.af_libs.superresolution.build_sr4x`` (the degradation of scripts/shift_ldm_sr.py:45,102) and the
+    ``H / Ht / H_pinv`` methods of ``build_sr_bicubic`` against the unmodified reference's outputs."""
+    from afldm.af_libs.superresolution import build_sr4x, build_sr_bicubic, build_sr_pool
+    from oracle import superres as OSR
+    g = golden("superres")
+    for n in (32, 64):
+        x = dev(g[f"x_{n}"])
+        for filt in ("bicubic", "pool"):
+            got = build_sr4x(DEV, filt, n)(x)
+            assert got.shape == x.shape
+            np.testing.assert_allclose(got.cpu().numpy(), g[f"sr4x_{filt}_{n}"], atol=3e-6)
+        hb = build_sr_bicubic(4, DEV, n)
+        y = hb.H(x)
+        np.testing.assert_allclose(y.cpu().numpy(), g[f"H_{n}"], atol=3e-6)
+        np.testing.assert_allclose(hb.Ht(y).cpu().numpy(), g[f"Ht_{n}"], atol=3e-6)
+        np.testing.assert_allclose(hb.H_pinv(y).cpu().numpy(), g[f"Hpinv_{n}"], atol=2e-4)
+        assert build_sr_pool(4, DEV, n).H(x).shape == (2, 3 * (n // 4) ** 2)
+    x = (torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(296)) * 2 - 1)
+    y = build_sr4x(DEV, "bicubic", 256)(x.to(DEV))
+    np.testing.assert_allclose(y[0, :, ::37, ::41].cpu().numpy(), g["rows_256"], atol=3e-6)
+    np.testing.assert_allclose(y.cpu().numpy(), OSR.sr4x(x.numpy()), atol=3e-6)
+    assert build_sr4x(DEV, "bicubic", 256)(x[0].to(DEV)).shape == (3, 256, 256)          # 3-D input (:300-303)
+    assert build_sr4x(DEV, "bicubic", 256)(x).is_cuda                                    # host input is moved, as :305 does

@@ -120,3 +120,21 @@ def test_shift_harness_matches_reference(golden):
     assert abs(float(S.mask_mse(a, b, m)) - float(g["mask_mse"])) < 1e-6
     assert abs(float(S.mask_psnr(a, b, m)) - float(g["mask_psnr"])) < 1e-5
     assert abs(float(S.psnr(a, b)) - float(g["psnr"])) < 1e-5
+
+
+def test_superresolution_operators_match_reference(golden):
+    """oracle/superres.py against the unmodified reference's ``build_sr4x`` / ``build_sr_bicubic(...).H``
+    (afldm/af_libs/superresolution.py:263-320): the x4 degradation of scripts/shift_ldm_sr.py."""
+    from oracle import superres as SR
+    g = golden("superres")
+    for n in (32, 64):
+        x = g[f"x_{n}"]
+        for filt in ("bicubic", "pool"):
+            np.testing.assert_allclose(SR.sr4x(x, filt), g[f"sr4x_{filt}_{n}"], atol=2e-6)
+        np.testing.assert_allclose(SR.degrade(x, "bicubic").reshape(2, -1), g[f"H_{n}"], atol=2e-6)
+    x = (torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(296)) * 2 - 1).numpy()
+    y = SR.sr4x(x, "bicubic")
+    assert abs(y.sum() - g["sum_256"][0]) < 2e-2 and abs(np.abs(y).sum() - g["sum_256"][1]) < 2e-2
+    np.testing.assert_allclose(y[0, :, ::37, ::41], g["rows_256"], atol=2e-6)
+    s = np.linalg.svd(SR.h_small_bicubic(256), compute_uv=False)
+    assert s.min() > 0.3            # nothing is cut at 3e-2 for the script's size: the operator IS the bicubic filter
