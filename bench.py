@@ -1014,7 +1014,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, sample = cpu_reference_rate(25.0, 1, 0)
+        rate, cores, sample = cpu_reference_rate(30.0, 8, 1)      # ~10-15 s of host work: 1 warm-up + 8 timed steps
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
