@@ -110,6 +110,7 @@ class VideoEquivariantEditingPipeline:
         self.encode_prompt_fn = encode_prompt
         self.attn_state = AttnState()
         self.replayed_launches = 0                # kernels launched through graph replays (the eager counter misses them)
+        self._captured_sig = None
         self._captured = {}                       # captured steps of the CUDA-graph path, per (steps, size, frames, ...)
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
 
@@ -289,6 +290,14 @@ class VideoEquivariantEditingPipeline:
         ori = self.unet.attn_processors
         do_cfg = neg is not None
         key = (n, size, num_frames, rest.shape[0], do_cfg, float(guidance_scale), str(dev))
+        # what the captured steps bake in besides the shapes: the storage / version of every parameter (the packed weight
+        # copies are rebuilt from them and the graphs hold raw pointers to those copies), the numeric class, the switches
+        sig = (tuple((p.data_ptr(), p._version) for p in self.unet.parameters()), ops.default_conv_algo(), ops.F16_CONV,
+               ops.F16_ATTENTION, ops.FUSE_GN_PROLOGUE, ops.FUSE_CONCAT, ops.SHORTCUT_SIDE_STREAM)
+        if sig != self._captured_sig:
+            torch.cuda.synchronize(dev)
+            self._captured.clear()
+            self._captured_sig = sig
         cached = self._captured.get(key)
         if cached is None:
             st = AttnState()
@@ -297,6 +306,7 @@ class VideoEquivariantEditingPipeline:
             cached = self._captured[key] = {"state": st, "steps": {},
                                             "procs": {k: CrossFrameAttnProcessor(st) for k in ori}}
             while len(self._captured) > 2:                              # graphs pin their activations: keep two shapes
+                torch.cuda.synchronize(dev)                             # nothing of the evicted graphs is still in flight
                 self._captured.pop(next(iter(self._captured)))
         st = self.attn_state = cached["state"]
         slots = st.slots

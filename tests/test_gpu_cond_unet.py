@@ -149,6 +149,15 @@ def test_video_pipeline_matches_oracle_loop():
     procs = next(iter(pipe._captured.values()))["procs"]
     assert all(len(p._pairs[0]) == 2 for p in procs.values() if p._pairs[0])
     torch.testing.assert_close(cap2.contiguous(), eag2.contiguous(), rtol=0, atol=1e-5)
+    # changed weights invalidate the captured steps (they hold pointers to packed copies of the old ones)
+    with torch.no_grad():
+        mine.conv_in.weight.mul_(1.05)
+    eag3 = pipe(frames, prompt_embeds=pos, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
+                strength=0.7, guidance_scale=7.5, output_type="latent").images
+    cap3 = pipe(frames, prompt_embeds=pos, negative_prompt_embeds=neg, inv_prompt_embeds=inv, num_inference_steps=6,
+                strength=0.7, guidance_scale=7.5, output_type="latent", use_cuda_graph=True).images
+    assert not torch.equal(eag3, lat)
+    torch.testing.assert_close(cap3.contiguous(), eag3.contiguous(), rtol=0, atol=1e-5)
     assert mine.attn_processors == before
     with pytest.raises(ValueError):
         pipe(frames, prompt="a red car", num_inference_steps=2)    # no text encoder in this build: embeddings required
