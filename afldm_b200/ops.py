@@ -726,9 +726,13 @@ def linear_rows(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     n = w.shape[0]
     y = torch.empty((m, n), dtype=torch.float32, device=x.device)
     L = _lib.lib()
-    _run("linear_rows", dict(M=m, K=k, N=n, bytes=4.0 * n * k),
-         lambda: L.afldm_linear_rows_f32(x.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr(), m, k, n,
-                                         ACT[act_in], ACT[act_out], _stream()), (x, w, bias, y))
+    rows = max(1, min(64, (200 * 1024) // (4 * k)))       # the kernel keeps its rows of x in shared memory: <= 64 at a time
+    for m0 in range(0, m, rows):
+        xs, ys = x[m0:m0 + rows], y[m0:m0 + rows]
+        mm = xs.shape[0]
+        _run("linear_rows", dict(M=mm, K=k, N=n, bytes=4.0 * n * k),
+             lambda xs=xs, ys=ys, mm=mm: L.afldm_linear_rows_f32(xs.data_ptr(), w.data_ptr(), _ptr(bias), ys.data_ptr(), mm, k, n,
+                                                                 ACT[act_in], ACT[act_out], _stream()), (xs, w, bias, ys))
     return y
 
 

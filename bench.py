@@ -455,31 +455,51 @@ def run_vae_workload(args, torch, dev):
     print(json.dumps(line), flush=True)
 
 
-def run_i2sb_workload(args, torch, dev):
-    """BASELINE config #5, one GPU's share: the FFHQ UNet architecture at 64 x 64 latents, B = 16, I2SB bridge (ODE form,
-    i2sb_pipeline.py:45-56), captured step.  99 UNet evaluations per 100-step run; `steps` of them are timed."""
-    from afldm_b200 import ops
+def run_i2sb_workload(args, torch, dev, dist=None, rank=0, world=1):
+    """BASELINE config #5: the FFHQ UNet architecture (the I2SB model is initialised from it) at 64 x 64 x 4 latents,
+    global batch ``--i2sb-batch`` (128 in BASELINE.json; default 16 = one GPU's share of the 8-GPU shard) cut into
+    contiguous slices over the ranks, I2SB bridge in ODE form (i2sb_pipeline.py:45-56), captured step; 99 UNet
+    evaluations per 100-step run, `steps` of them are timed.  No collective in the step loop; the tail - alias-free VAE
+    decode to 512 x 512 + ONE all-gather of the decoded frames + copy to the host - is timed once (``e2e.tail``)."""
+    from afldm_b200 import ops, parallel
     from afldm_b200.pipelines import I2SBLDMPipeline
     from afldm_b200.schedulers import I2SBScheduler
-    from afldm_b200.models import UNet2DModel
+    from afldm_b200.models import AliasFreeAutoencoderKL, UNet2DModel
     from afldm_b200.af_modules.af_api import make_af_unet
     ops.set_default_conv_algo(args.conv_algo)
     torch.manual_seed(0)
     unet = UNet2DModel.from_config()
     make_af_unet(unet)
-    pipe = I2SBLDMPipeline(None, unet, I2SBScheduler.from_config()).to(dev)
+    vae = None if args.no_vae else AliasFreeAutoencoderKL.from_config()
+    pipe = I2SBLDMPipeline(vae, unet, I2SBScheduler.from_config()).to(dev)
+    total = args.i2sb_batch
     g = torch.Generator().manual_seed(0)
-    lat = torch.randn(BATCH, 4, 64, 64, generator=g)
+    lat_all = torch.randn(total, 4, 64, 64, generator=g)
+    lo, hi = parallel.shard_bounds(total, rank, world)
+    lat = lat_all[lo:hi].contiguous()
+    nb = hi - lo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     records = []
     ops.record_to(records)
     with torch.no_grad():
         pipe.unet(lat.to(dev), 981)
     ops.record_to(None)
-    gd = pipe.graphed(BATCH, size=64)
+    gd = pipe.graphed(nb, size=64)
     pipe.scheduler.set_timesteps(100)
     ts = [int(t) for t in pipe.scheduler.timesteps][:99]
     table = torch.tensor([[1.0, float(pipe.scheduler.coefficients(t)[0])] for t in ts], dtype=torch.float32, device=dev)
-    tt = torch.tensor(ts, dtype=torch.float32, device=dev)[:, None].expand(-1, BATCH).contiguous()
+    tt = torch.tensor(ts, dtype=torch.float32, device=dev)[:, None].expand(-1, nb).contiguous()
     gd.x.copy_(ops.nhwc(lat.to(dev)))
 
     def run(n, first):
@@ -489,16 +509,17 @@ def run_i2sb_workload(args, torch, dev):
             gd.replay()
 
     run(args.warmup, 0)
-    torch.cuda.synchronize()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index or 0) as clk:
         ev0.record()
         run(args.steps, args.warmup)
         ev1.record()
-        ev1.synchronize()
-    ms = ev0.elapsed_time(ev1) / args.steps
+        barrier()
+    ms = allmax(ev0.elapsed_time(ev1)) / args.steps
     h_in = lat.pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
+    barrier()
     ev0.record()
     for i in range(args.steps):
         gd.x.copy_(ops.nhwc(h_in.to(dev, non_blocking=True)))
@@ -508,20 +529,47 @@ def run_i2sb_workload(args, torch, dev):
         h_out.copy_(ops.to_nchw_contiguous(gd.x), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     ev1.record()
-    ev1.synchronize()
-    e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    barrier()
+    e2e_ms = allmax(ev0.elapsed_time(ev1)) / args.steps
+
+    tail = None
+    if vae is not None:
+        # the pipeline tail: decode this rank's latents (4 at a time: the 512 x 512 planes), gather, copy out - once
+        def run_tail():
+            x = ops.to_nchw_contiguous(gd.x)
+            frames = torch.cat([pipe.decode_latents(x[i:i + 4]) for i in range(0, nb, 4)], dim=0)
+            allf = parallel.gather_frames(frames.contiguous(), total)
+            return allf.to("cpu") if rank == 0 else None
+        with torch.no_grad():
+            run_tail()
+            barrier()
+            ev0.record()
+            out = run_tail()
+            ev1.record()
+            barrier()
+        tail = {"what": f"alias-free VAE decode of the rank's {nb} latents to 3x512x512 (operator-matrix form above 128 x 128 planes) "
+                        "+ ONE all-gather of the decoded frames + device-to-host copy on rank 0; once per run, max over ranks",
+                "ms": allmax(ev0.elapsed_time(ev1)), "gathered_bytes": total * 3 * 512 * 512 * 4,
+                "finite": bool(torch.isfinite(out).all().item()) if rank == 0 else None,
+                "frames": list(out.shape) if rank == 0 else None}
+    if rank != 0:
+        barrier()                       # leave together with rank 0 (it times the kernels one by one first)
+        return
     pk = peaks()
     agg = aggregate(time_records(records, torch, dev, reps=3))
+    barrier()
     roof, fir = rooflines(agg, pk, step_ms=ms)
     tot = sum(a["ms_hot"] for a in agg.values())
-    line = {"metric": "i2sb_unet_steps_per_sec", "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": "i2sb_unet_steps_per_sec", "value": 1000.0 / ms, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "TF32 class (see the headline line)", "data": "synthetic",
-            "config": {"workload": "AF-I2SB SR UNet (FFHQ UNet architecture, 256.4M params) at 64x64x4 latents, B=16 per GPU "
-                                   "(config #5: B=128 over 8 GPUs), I2SB ODE update, CUDA-graph step", "global_batch": BATCH,
+            "config": {"workload": f"AF-I2SB SR UNet (FFHQ UNet architecture, 256.4M params) at 64x64x4 latents, global batch {total} "
+                                   f"sharded {nb} per GPU (config #5: B=128 over 8 GPUs), I2SB ODE update, CUDA-graph step; one step = one "
+                                   "bridge step of the whole batch", "global_batch": total, "per_gpu_batch": nb,
                        "l2": "1.03 GB of weights per step >> 126 MB L2"},
             "clocks": clk.summary(), "finite": bool(torch.isfinite(gd.x).all().item()),
-            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h_in.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4},
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": h_in.numel() * 4,
+                    "d2h_bytes_per_step": h_out.numel() * 4, "tail": tail},
             "gpu_launches": gd.launches_per_step * args.steps, "launches_per_step": gd.launches_per_step,
             "roofline": roof, "roofline_filtered_act": fir,
             "breakdown": {k: {"launches": v["launches"], "ms": round(v["ms_hot"], 3), "share": round(v["ms_hot"] / tot, 4)}
@@ -767,6 +815,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d", "shift_ldm", "video"])
     ap.add_argument("--video-frames", type=int, default=16)
+    ap.add_argument("--watchdog", type=int, default=1500,
+                    help="seconds after which a stuck rank prints its Python stacks and exits (0 = off)")
+    ap.add_argument("--i2sb-batch", type=int, default=16,
+                    help="config #5 global batch (BASELINE: 128 over 8 GPUs; default 16 = one GPU's share), sharded over the ranks")
     ap.add_argument("--video-eager", action="store_true", help="config #4 with eager launches instead of captured steps")
     ap.add_argument("--conv-algo", default=os.environ.get("AFLDM_CONV_ALGO", "tf32"), choices=["simt", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -791,11 +843,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.watchdog > 0:
+        # a rank that stops making progress (a hung kernel, a collective whose peer died) dumps every thread's stack
+        # and exits instead of holding the box until the caller's limit
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: afldm_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if args.workload == "video":
+    if args.workload in ("video", "i2sb"):
         if world > 1:
             os.environ.setdefault("NCCL_DEBUG", "WARN")
             sys.stdout.flush()
@@ -809,7 +866,10 @@ def main():
                 sys.stdout.flush()
                 os.dup2(saved_fd, 1)
                 os.close(saved_fd)
-        run_video_workload(args, torch, dev, dist, rank, world)
+        if args.workload == "video":
+            run_video_workload(args, torch, dev, dist, rank, world)
+        else:
+            run_i2sb_workload(args, torch, dev, dist, rank, world)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -817,7 +877,7 @@ def main():
         if rank != 0:
             return
         ops.set_default_conv_algo(args.conv_algo)
-        return {"vae_decode": run_vae_workload, "i2sb": run_i2sb_workload, "upfirdn2d": run_upfirdn2d_workload,
+        return {"vae_decode": run_vae_workload, "upfirdn2d": run_upfirdn2d_workload,
                 "shift_ldm": run_shift_workload}[args.workload](args, torch, dev)
     if world > 1:
         # NCCL prints its version banner to stdout when the communicator is created: route fd 1 to stderr around the

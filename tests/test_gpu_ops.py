@@ -426,3 +426,10 @@ def test_upfirdn2d_matches_reference_golden(golden):
     xr = randn(2, 3, 11, 13, seed=8)
     want = OU.upfirdn2d(xr.cpu().numpy(), fa.cpu().numpy(), 2, 3, (3, 2, 1, 4), False, 0.7)
     np.testing.assert_allclose(ops.upfirdn2d(xr, fa, 2, 3, (3, 2, 1, 4), False, 0.7).cpu().numpy(), want, atol=2e-6)
+
+
+def test_linear_rows_more_than_64_rows():
+    """The time-embedding MLP at batch 128 (config #5 on one GPU): rows are processed 64 at a time."""
+    x, w, b = randn(130, 192, seed=1), randn(768, 192, seed=2) * 0.1, randn(768, seed=3)
+    got = ops.linear_rows(x, w, b, act_out="silu")
+    torch.testing.assert_close(got, F.silu(x @ w.t() + b), rtol=0, atol=2e-5)
