@@ -970,11 +970,12 @@ TcPlan tc_plan(int B, int H, int W, int Cin, int Cout, int ks, bool f16 = false)
     // share an SM - two CTAs of this launch, the head of a PDL-overlapped successor, a conv_shortcut on the side
     // stream.  A CTA pair (cta_group::2) that holds its columns on one SM while its peer waits on the other can dead-lock
     // against a pair of another kernel doing the same (seen on B200: an intermittent hang of the SD-1.5 video loop).
-    // Shared memory is the resource that decides co-residency, so a CTA with c columns asks for enough of it that at
-    // most 512 / c such CTAs fit on an SM (228 KB, 1 KB reserved per CTA).
+    // Shared memory is the resource that decides co-residency, so every CTA asks for shared memory IN PROPORTION to its
+    // columns: 454 B per column including the 1 KB the hardware reserves per CTA.  CTAs that fit on one SM (228 KB) then
+    // hold at most 233472 / 454 = 514 columns - column counts are powers of two >= 32, so at most 512 - whatever mix of
+    // launches they come from; 256 columns cost exactly the two-per-SM budget (115200 B), 512 columns 231424 B.
     {
-        const int kmax = 512 / p.tmem_cols;
-        const size_t floor_bytes = (size_t)(233472 / (kmax + 1)) - 1024 + 16;
+        const size_t floor_bytes = (size_t)p.tmem_cols * 454 - 1024;
         if (p.smem_bytes < floor_bytes) p.smem_bytes = floor_bytes;
     }
     p.ok = true;

@@ -534,10 +534,11 @@ def run_i2sb_workload(args, torch, dev, dist=None, rank=0, world=1):
 
     tail = None
     if vae is not None:
-        # the pipeline tail: decode this rank's latents (4 at a time: the 512 x 512 planes), gather, copy out - once
+        # the pipeline tail: decode this rank's latents one image at a time (as the reference's loops do,
+        # video_equiv_editing_pipeline.py:721-727; the 512 x 512 planes of one image fill the GPU), gather, copy out - once
         def run_tail():
             x = ops.to_nchw_contiguous(gd.x)
-            frames = torch.cat([pipe.decode_latents(x[i:i + 4]) for i in range(0, nb, 4)], dim=0)
+            frames = torch.cat([pipe.decode_latents(x[i:i + 1]) for i in range(nb)], dim=0)
             allf = parallel.gather_frames(frames.contiguous(), total)
             return allf.to("cpu") if rank == 0 else None
         with torch.no_grad():
