@@ -119,6 +119,44 @@ def bilinear_matrix(n: int, t: float) -> Tuple[np.ndarray, np.ndarray]:
     return m, valid
 
 
+def lanczos_matrix(n: int, t: float, a: int = 3) -> Tuple[np.ndarray, np.ndarray]:
+    """One axis of StyleGAN3's ``apply_fractional_translation`` (af_libs/equivariance.py:68-103, what
+    ``ImageShifter('lanczos')`` calls with tx = tj / w, ty = ti / h, shifters.py:159-162): output sample X is
+    sum_m x[m] L(X - m - t) / S over the 2a taps X - m - floor(t) in {-(a-1) .. a}, L(u) = sinc(u) sinc(u / a),
+    S = the sum of the 2a tap values (the filter is normalised before it meets the border), zeros outside the image;
+    columns outside [max(floor(t) - a + 1, 0), min(floor(t) + a, 0) + n) are zero.  The offset goes through the same
+    fp32 value as the reference's ``torch.as_tensor(tx * W).to(float32)``.  Returns (matrix [n, n] fp64, valid [n] bool:
+    the reference's mask, ones on [max(floor(t) + a, 0), min(floor(t) - a + 1, 0) + n))."""
+    f32 = np.float32
+    t32 = f32((t / n) * n)
+    it = int(np.floor(t32))
+    ft = f32(t32 - f32(it))
+    b = a - 1
+    taps = np.arange(-b, a + 1 - 0, dtype=np.float32)[:2 * a]                  # -(a-1) .. a
+    u = (taps - ft).astype(np.float32)
+
+    def sinc32(v):
+        y = np.abs(v.astype(np.float32) * f32(np.pi))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            z = np.sin(y) / np.maximum(y, f32(1e-30))
+        return np.where(y < 1e-30, f32(1), z).astype(np.float32)
+
+    f = (sinc32(u) * sinc32(u / f32(a))).astype(np.float32)
+    f = (f / f.sum(dtype=np.float32)).astype(np.float64)
+    m = np.zeros((n, n))
+    z0, z1 = max(it - b, 0), min(it + a, 0) + n
+    for X in range(z0, max(z0, z1)):
+        for k in range(2 * a):
+            src = X - it - int(taps[k])
+            if 0 <= src < n:
+                m[X, src] += f[k]
+    valid = np.zeros(n, dtype=bool)
+    m0, m1 = max(it + a, 0), min(it - b, 0) + n
+    if m0 < m1:
+        valid[m0:m1] = True
+    return m, valid
+
+
 def fourier_matrices(n: int, t: float) -> Tuple[np.ndarray, np.ndarray]:
     """One axis of ``fourier_shift_batch`` (shifters.py:101-132): multiplication of the DFT by exp(-2 pi i t f_k),
     f = fftfreq(n).  Returns the real and imaginary circulants (A_r, A_i): the reference keeps the REAL part of the 2-D
@@ -162,8 +200,8 @@ def fourier_shift_batch(image: torch.Tensor, shift_x, shift_y, device="cuda") ->
 
 
 class ImageShifter:
-    """``ImageShifter(filter=None, upsample_ratio=None)`` (shifters.py:135-206).  'lanczos' (StyleGAN3's
-    ``apply_fractional_translation``) is not provided."""
+    """``ImageShifter(filter=None, upsample_ratio=None)`` (shifters.py:135-206): bilinear (default), lanczos, ideal,
+    ideal_crop, fourier, fourier_crop - every filter is a pair of operator matrices applied by one launch pair."""
 
     class BgType(Enum):
         NO_BG = 0
@@ -175,9 +213,6 @@ class ImageShifter:
         if filter is None:
             filter = "bilinear"                             # the reference's default (:143-144)
         assert filter in FILTER_CHOICES, f"Wrong filter type {filter}"
-        if filter == "lanczos":
-            raise NotImplementedError("ImageShifter('lanczos') needs StyleGAN3's apply_fractional_translation, "
-                                      "which is outside the AF-LDM path of this build")
         if filter in ("ideal", "ideal_crop"):
             assert upsample_ratio is not None
             if int(upsample_ratio) < 1:
@@ -187,7 +222,7 @@ class ImageShifter:
 
     def shift(self, img: torch.Tensor, ti: float, tj: float) -> Tuple[torch.Tensor, torch.Tensor]:
         """img [B,C,H,W] fp32 CUDA -> (warped [B,C,H,W], mask); rows move by ti, columns by tj.  The mask is
-        [B,C,H,W] for the ideal / fourier filters and [B,1,H,W] for the bilinear warp, as in the reference."""
+        [B,C,H,W] for the ideal / fourier filters and [B,1,H,W] for the bilinear / lanczos warps, as in the reference."""
         warped, masks = self.shift_batch(img, [(ti, tj)])
         return warped[0], masks[0]
 
@@ -217,9 +252,11 @@ class ImageShifter:
                 return outs, torch.ones_like(outs)
             masks = torch.stack([gen_valid_mask((b, c, h, w), ti, tj) for ti, tj in shifts]).to(x.device)
             return outs * masks, masks
-        # bilinear (default): uniform flow warp, zeros outside, mask = sampled position inside the image
-        rows = [bilinear_matrix(h, ti) for ti, _ in shifts]
-        cols = [bilinear_matrix(w, tj) for _, tj in shifts]
+        # bilinear (default): uniform flow warp, zeros outside, mask = sampled position inside the image;
+        # lanczos: the 6-tap windowed-sinc translation of StyleGAN3's equivariance metrics, mask = full filter support
+        axis = lanczos_matrix if self.filter == "lanczos" else bilinear_matrix
+        rows = [axis(h, ti) for ti, _ in shifts]
+        cols = [axis(w, tj) for _, tj in shifts]
         out = _sep(x, np.stack([m for m, _ in rows]), np.stack([m for m, _ in cols]))
         masks = torch.stack([torch.from_numpy(np.outer(vr, vc).astype(np.float32)) for (_, vr), (_, vc) in zip(rows, cols)])
         masks = masks.view(len(shifts), 1, 1, h, w).expand(len(shifts), b, 1, h, w).contiguous().to(x.device)

@@ -123,6 +123,12 @@ def main():
     sh["fourier_img"] = RS.fourier_shift_batch(img, 0.75, -2.3, device="cpu").numpy()
     w, m = RS.ImageShifter("fourier_crop").shift(img, 1.5, 0.25)
     sh["fcrop_img"], sh["fcrop_mask"] = w.contiguous().numpy(), m.numpy()
+    lz = RS.ImageShifter("lanczos")
+    for k, (ti, tj) in enumerate([(0.0, 0.5), (2.75, -1.5), (-3.3, 4.9), (1 / 3, -2 / 3), (23.5, -26.0)]):
+        w, m = lz.shift(img, ti, tj)
+        sh[f"lz{k}_t"] = np.array([ti, tj])
+        sh[f"lz{k}_img"] = w.contiguous().numpy()
+        sh[f"lz{k}_mask"] = m.numpy()
     a, b = randn((2, 3, 16, 16), 3), randn((2, 3, 16, 16), 4)
     m = RS.gen_valid_mask(a.shape, 2.5, -1.25)
     sh["m_a"], sh["m_b"], sh["m_mask"] = a.numpy(), b.numpy(), m.numpy()

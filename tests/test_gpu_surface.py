@@ -224,3 +224,18 @@ def test_superresolution_x4_degradation(golden):
     np.testing.assert_allclose(y.cpu().numpy(), OSR.sr4x(x.numpy()), atol=3e-6)
     assert build_sr4x(DEV, "bicubic", 256)(x[0].to(DEV)).shape == (3, 256, 256)          # 3-D input (:300-303)
     assert build_sr4x(DEV, "bicubic", 256)(x).is_cuda                                    # host input is moved, as :305 does
+
+
+def test_lanczos_shifter_vs_reference_goldens(golden):
+    """``ImageShifter('lanczos')`` on the device against the unmodified reference (shifters.py:159-162)."""
+    from afldm.shift_utils.shifters import ImageShifter
+    g = golden("shift")
+    img = dev(g["img"])
+    sh = ImageShifter("lanczos")
+    for k in range(5):
+        ti, tj = (float(v) for v in g[f"lz{k}_t"])
+        w, m = sh.shift(img, ti, tj)
+        np.testing.assert_allclose(w.cpu().numpy(), g[f"lz{k}_img"], atol=3e-6)
+        assert m.shape == (2, 1, 24, 24) and np.array_equal(m.cpu().numpy(), g[f"lz{k}_mask"])
+    ws, ms = sh.shift_batch(img, [tuple(float(v) for v in g[f"lz{k}_t"]) for k in range(5)])
+    np.testing.assert_allclose(ws[2].cpu().numpy(), g["lz2_img"], atol=3e-6)

@@ -138,3 +138,17 @@ def test_superresolution_operators_match_reference(golden):
     np.testing.assert_allclose(y[0, :, ::37, ::41], g["rows_256"], atol=2e-6)
     s = np.linalg.svd(SR.h_small_bicubic(256), compute_uv=False)
     assert s.min() > 0.3            # nothing is cut at 3e-2 for the script's size: the operator IS the bicubic filter
+
+
+def test_lanczos_shifter_matches_reference(golden):
+    """oracle/shift.lanczos_shift against the unmodified reference's ``ImageShifter('lanczos').shift``
+    (shifters.py:159-162 -> StyleGAN3 ``apply_fractional_translation``, af_libs/equivariance.py:68-103), including a
+    shift that leaves nothing of the image."""
+    g = golden("shift")
+    img = torch.from_numpy(g["img"])
+    for k in range(5):
+        ti, tj = g[f"lz{k}_t"]
+        w, m = S.lanczos_shift(img, float(ti), float(tj))
+        np.testing.assert_allclose(w.numpy(), g[f"lz{k}_img"], atol=3e-6)
+        assert np.array_equal(m.numpy(), g[f"lz{k}_mask"])
+    assert g["lz4_mask"].sum() == 0 and np.abs(g["lz4_img"]).max() < 1e-6
