@@ -194,17 +194,20 @@ class VideoEquivariantEditingPipeline:
     def edit_latents(self, frame_latents: torch.Tensor, pos: torch.Tensor, neg: Optional[torch.Tensor], inv: torch.Tensor,
                      num_inference_steps: int = 50, strength: float = -1, guidance_scale: float = 7.5,
                      frame_batch: Optional[int] = None, start_latents: Optional[torch.Tensor] = None,
-                     reference_latent: Optional[torch.Tensor] = None, use_cuda_graph: bool = False) -> torch.Tensor:
+                     reference_latent: Optional[torch.Tensor] = None, use_cuda_graph: bool = False,
+                     reference_start_latent: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The latent-space part of ``__call__`` (:503-697) on VAE-encoded frames [F,4,h,w]: cross-frame processors,
         per-frame inversion, STORE pass of the reference frame, LOAD denoising of every frame.
 
         ``reference_latent`` [1,4,h,w]: the frame whose attention maps everybody attends to (default: frame 0 of
         ``frame_latents``).  A rank that holds only a SLICE of the video passes the encoded frame 0 here and re-runs its
         inversion + STORE pass locally - ~1/F of the work - instead of receiving the maps of 2 x 16 attention layers x
-        steps from rank 0.  ``use_cuda_graph``: replay captured steps (``_edit_latents_captured``)."""
+        steps from rank 0; with caller-supplied ``start_latents`` it also passes the reference frame's
+        start latent as ``reference_start_latent`` so that its STORE pass starts where rank 0's does.
+        ``use_cuda_graph``: replay captured steps (``_edit_latents_captured``)."""
         if use_cuda_graph and (frame_batch is None or frame_batch >= frame_latents.shape[0]):
             return self._edit_latents_captured(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
-                                               start_latents, reference_latent)
+                                               start_latents, reference_latent, reference_start_latent)
         dev = self.device
         frame_latents = frame_latents.to(device=dev, dtype=torch.float32)
         num_frames = frame_latents.shape[0]
@@ -238,6 +241,8 @@ class VideoEquivariantEditingPipeline:
             st.reset()
             st.set_store_id(0)
             x = lat[:1] if own_reference else lat0
+            if not own_reference and reference_start_latent is not None:
+                x = reference_start_latent.to(device=dev, dtype=torch.float32)
             for t in ts:
                 st.set_timestep(t)
                 eps = self._eps(x, t, pos, guidance_scale, neg)
@@ -256,7 +261,7 @@ class VideoEquivariantEditingPipeline:
 
     @torch.no_grad()
     def _edit_latents_captured(self, frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
-                               start_latents, reference_latent) -> torch.Tensor:
+                               start_latents, reference_latent, reference_start_latent=None) -> torch.Tensor:
         """``edit_latents`` with every UNet evaluation + update replayed from CUDA graphs: the cross-frame maps live in
         device tables indexed by the step (``AttnState.enable_slots``), timestep / coefficients / slot are device
         scalars refreshed between replays.  Four captured steps: inversion (reference frame: STORE; other frames: LOAD,
@@ -344,8 +349,10 @@ class VideoEquivariantEditingPipeline:
                 lat = start_latents.to(device=dev, dtype=torch.float32)
             st.reset()
             st.set_store_id(0)
-            run(step_for("den_store", 1, pos, neg if do_cfg else None), lat[:1] if own_reference else lat0,
-                list(range(n)), den_coef)
+            ref_start = lat[:1] if own_reference else lat0
+            if not own_reference and reference_start_latent is not None:
+                ref_start = reference_start_latent.to(device=dev, dtype=torch.float32)
+            run(step_for("den_store", 1, pos, neg if do_cfg else None), ref_start, list(range(n)), den_coef)
             st.to_load()
             lat = run(step_for("den_load", num_frames, pos, neg if do_cfg else None), lat, list(range(n)), den_coef)
         finally:
@@ -380,7 +387,8 @@ class VideoEquivariantEditingPipeline:
         reference = None if lo == 0 else self.image2latent(images[0])
         lat = self.edit_latents(frame_latents, pos, neg, inv, num_inference_steps, strength, guidance_scale,
                                 frame_batch=frame_batch, start_latents=None if latents is None else latents[lo:hi],
-                                reference_latent=reference, use_cuda_graph=use_cuda_graph)
+                                reference_latent=reference, use_cuda_graph=use_cuda_graph,
+                                reference_start_latent=None if (latents is None or lo == 0) else latents[:1])
 
         if output_type == "latent":
             image = lat if shard is None else parallel.gather_frames(lat.contiguous(), num_frames)
