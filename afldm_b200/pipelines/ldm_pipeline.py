@@ -363,19 +363,32 @@ class MyLDMPipeline:
         return self.vae.decode(latents / self.vae.config.scaling_factor).sample
 
     @torch.no_grad()
-    def ddim_inversion(self, latent: torch.Tensor, bar: bool = True) -> torch.Tensor:
-        """ldm_pipeline.py:133-160: deterministic DDIM run backwards over ``scheduler.timesteps``."""
+    def ddim_inversion(self, latent: torch.Tensor, bar: bool = True, use_cuda_graph: bool = False) -> torch.Tensor:
+        """ldm_pipeline.py:133-160: deterministic DDIM run backwards over ``scheduler.timesteps``.  The update has the
+        form of the sampling step, latent <- cx latent + ce eps(latent, t), so ``use_cuda_graph=True`` replays the
+        captured step of ``denoise`` with the inversion's coefficients (default processors or slot-mode CFA only)."""
         sch = self.scheduler
         timesteps = sch.timesteps.flip(0)
         latent = latent.to(device=self.device, dtype=torch.float32)
+        coefs = []
         for i, t in enumerate(timesteps):
             a_t = sch.alphas_cumprod[int(t)]
             a_prev = sch.alphas_cumprod[int(timesteps[i - 1])] if i > 0 else sch.final_alpha_cumprod
             mu, mu_prev = a_t ** 0.5, a_prev ** 0.5
             sigma, sigma_prev = (1 - a_t) ** 0.5, (1 - a_prev) ** 0.5
-            eps = self.unet(latent, int(t)).sample
             # latent' = mu * (latent - sigma_prev * eps) / mu_prev + sigma * eps
-            cx = float(mu / mu_prev)
-            ce = float(sigma - mu * sigma_prev / mu_prev)
+            coefs.append((float(mu / mu_prev), float(sigma - mu * sigma_prev / mu_prev)))
+        if use_cuda_graph and graph_capturable(self.unet) and self._attn_state() is None:
+            g = self.graphed(latent.shape[0], size=latent.shape[-1])
+            table = torch.tensor(coefs, dtype=torch.float32, device=self.device)
+            tt = timesteps.to(device=self.device, dtype=torch.float32)[:, None].expand(-1, latent.shape[0]).contiguous()
+            g.x.copy_(ops.nhwc(latent))
+            for i in range(len(coefs)):
+                g.t.copy_(tt[i])
+                g.coef.copy_(table[i])
+                g.replay()
+            return ops.to_nchw_contiguous(g.x)
+        for (cx, ce), t in zip(coefs, timesteps):
+            eps = self.unet(latent, int(t)).sample
             latent = ops.nchw_view(ops.axpby(ops.nhwc(latent), ops.nhwc(eps), cx, ce))
         return ops.to_nchw_contiguous(ops.nhwc(latent))

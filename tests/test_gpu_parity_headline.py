@@ -129,6 +129,9 @@ def test_ddim_inversion_vs_oracle(unets, algo, tol):
     mx, mean, rel = err(got, want)
     print(f"[{algo}] ddim_inversion: max|d| {mx:.3e} mean {mean:.3e} rel-rms {rel:.3e}")
     assert mx < tol, (algo, mx)
+    # the same loop replayed from the captured step (coefficients of the inversion in the device table)
+    cap = pipe.ddim_inversion(x, bar=False, use_cuda_graph=True)
+    torch.testing.assert_close(cap, got, rtol=0, atol=2e-5)
     # inversion followed by sampling returns to the start (the scripts' real-image path, shift_ldm_ffhq.py:110-116)
     if algo == "simt":
         back = pipe.denoise(got, 10, use_cuda_graph=False)
