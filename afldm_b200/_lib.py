@@ -45,6 +45,7 @@ SIGNATURES = {
     "afldm_affine_act_gn_f16out": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p]),
     "afldm_conv2d_workspace_floats": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "afldm_conv2d_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "afldm_conv2d_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)]),
     "afldm_conv2d_gn_slots": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "afldm_conv2d_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "afldm_conv2d_f16in_f32": (_i, [_p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),

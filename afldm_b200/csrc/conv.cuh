@@ -28,6 +28,8 @@ void splitk_reduce_launch(const float* ws, int splitk, const float* bias, const 
 
 // Whether the tcgen05 / TMA path covers this shape (x_half: fp16 operands, 64-channel stages).
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int ks, int x_half = 0);
+// host-side view of the launch plan: {TMEM columns, dynamic shared-memory bytes, CTAs, CTA-pair mode, BN, K splits, ring stages, halo mode}
+bool conv_tc_plan_query(int B, int H, int W, int Cin, int Cout, int ks, int x_half, int out[8]);
 // tcgen05 / TMA path.  Returns false (and leaves *floats alone) when the shape is not covered.
 bool conv_tc_workspace_floats(int B, int H, int W, int Cin, int Cout, int ks, size_t* floats, int x_half = 0);
 // Number of GroupNorm partial-sum slots per image the tensor-core path emits for this shape

@@ -39,6 +39,12 @@ extern "C" int afldm_conv2d_supported(int B, int H, int W, int Cin, int Cout, in
     return 0;
 }
 
+extern "C" int afldm_conv2d_plan(int B, int H, int W, int Cin, int Cout, int ksize, int algo, int* plan8) {
+    if (plan8 == nullptr || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return AFLDM_E_ARG;
+    if (algo != AFLDM_CONV_TCGEN05_TF32 && algo != AFLDM_CONV_TCGEN05_F16) return AFLDM_E_NOKERNEL;
+    return conv_tc_plan_query(B, H, W, Cin, Cout, ksize, algo == AFLDM_CONV_TCGEN05_F16, plan8) ? 0 : AFLDM_E_NOKERNEL;
+}
+
 extern "C" int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int ksize, int algo) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
     if (algo != AFLDM_CONV_TCGEN05_TF32 && algo != AFLDM_CONV_TCGEN05_F16) return 0;

@@ -994,6 +994,14 @@ int conv_tc_gn_slots(int B, int H, int W, int Cin, int Cout, int ks, int x_half)
     return (HW == 64 || HW == 32) ? 1 : 0;               // tiles of whole images aligned to the epilogue's row quarters
 }
 
+bool conv_tc_plan_query(int B, int H, int W, int Cin, int Cout, int ks, int x_half, int out[8]) {
+    const TcPlan p = tc_plan(B, H, W, Cin, Cout, ks, x_half != 0);
+    if (!p.ok) return false;
+    out[0] = p.tmem_cols; out[1] = (int)p.smem_bytes; out[2] = p.grid_ctas; out[3] = p.two;
+    out[4] = p.BN; out[5] = p.splitk; out[6] = p.stages; out[7] = p.halo;
+    return true;
+}
+
 bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int ks, int x_half) {
     return tc_plan(B, H, W, Cin, Cout, ks, x_half != 0).ok;
 }

@@ -209,6 +209,14 @@ AFLDM_API int afldm_conv2d_gn_slots(int B, int H, int W, int Cin, int Cout, int 
 /* 1 when `algo` has a kernel for this shape (host-side plan only, no launch): a producer asks this before it decides to
  * store an activation as fp16 for afldm_conv2d_f16in_f32 (algo = AFLDM_CONV_TCGEN05_F16). */
 AFLDM_API int afldm_conv2d_supported(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
+
+/* Host-side query (no launch, works without a GPU): the launch plan of the tcgen05 convolution for this layer,
+ * plan8 = {TMEM columns per CTA, dynamic shared-memory bytes per CTA, CTAs, CTA-pair mode (cta_group::2), tile width BN,
+ * K splits, ring stages, halo mode}.  Exposes the invariant the library relies on: every plan asks for at least
+ * 454 B of shared memory per TMEM column (1 KB per-CTA reserve included), so CTAs that share an SM (228 KB) never hold
+ * more than 512 columns between them and tcgen05.alloc never blocks.  AFLDM_E_NOKERNEL when the
+ * shape is outside the tcgen05 family. */
+AFLDM_API int afldm_conv2d_plan(int B, int H, int W, int Cin, int Cout, int ksize, int algo, int* plan8);
 AFLDM_API size_t afldm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int algo);
 AFLDM_API int afldm_conv2d_f32(const float* x, int x_pitch, const float* w, const float* bias,
                      const float* row_add, int row_add_pitch, const float* residual, int res_pitch,

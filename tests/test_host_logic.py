@@ -217,3 +217,42 @@ def test_fp16_weight_pack_is_cached_and_invalidated():
         conv.weight.mul_(2.0)                                                # in-place update bumps the version
     w16b = conv_params_f16(conv)[0]
     assert w16b is not w16 and torch.equal(w16b, conv_params(conv)[0].half())
+
+
+def test_conv_plans_never_oversubscribe_tmem():
+    """Host-side invariant behind the hang fix of DESIGN.md section 3: every tcgen05 convolution plan requests shared
+    memory in proportion to its TMEM columns (>= 454 B per column, the 1 KB per-CTA reserve included), so whatever mix
+    of conv CTAs fits on one SM (228 KB of shared memory) holds at most 512 columns and `tcgen05.alloc` never blocks.
+    Checked over the layer shapes of all five BASELINE configurations (and more), both operand classes; no GPU needed."""
+    import ctypes as C
+    from afldm_b200 import _lib
+    L = _lib.lib()
+    plan = (C.c_int * 8)()
+    SM_SMEM, RESERVE, MAX_DYN = 233472, 1024, 232448
+    chans = (32, 64, 128, 192, 256, 320, 384, 512, 576, 640, 768, 960, 1152, 1280, 1536, 1920, 2560, 4096)
+    seen, pairs, widest = 0, 0, 0
+    for algo in (1, 2):
+        for ks in (1, 3):
+            for b in (1, 2, 4, 16, 32, 128):
+                for n in (2, 4, 8, 16, 32, 64, 128, 256, 512):
+                    if b * n * n > (1 << 25):
+                        continue
+                    for cin in chans:
+                        for cout in (4, 32) + chans:
+                            if L.afldm_conv2d_plan(b, n, n, cin, cout, ks, algo, plan) != 0:
+                                continue
+                            cols, smem, ctas, two = plan[0], plan[1], plan[2], plan[3]
+                            seen += 1
+                            pairs += two
+                            widest = max(widest, cols)
+                            assert cols in (32, 64, 128, 256, 512), (b, n, cin, cout, ks, algo, cols)
+                            assert smem <= MAX_DYN and ctas >= 1
+                            assert smem + RESERVE >= 454 * cols, (b, n, cin, cout, ks, algo, cols, smem)
+                            if two:
+                                assert ctas % 2 == 0
+    assert seen > 5000 and pairs > 500 and widest >= 256
+    # the arithmetic of the rule: CTAs that fit together have sum(smem + reserve) <= 228 KB, hence sum(cols) <= 514,
+    # and column counts are multiples of 32
+    assert SM_SMEM // 454 < 512 + 32
+    assert L.afldm_conv2d_plan(16, 32, 32, 192, 192, 3, 0, plan) == -3          # the exact-FMA class has no such plan
+    assert L.afldm_conv2d_plan(16, 32, 32, 100, 192, 3, 1, plan) == -3          # outside the tcgen05 family
