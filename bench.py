@@ -817,7 +817,8 @@ def main():
     ap.add_argument("--workload", default="unet", choices=["unet", "vae_decode", "i2sb", "upfirdn2d", "shift_ldm", "video"])
     ap.add_argument("--video-frames", type=int, default=16)
     ap.add_argument("--watchdog", type=int, default=1500,
-                    help="seconds after which a stuck rank prints its Python stacks and exits (0 = off)")
+                    help="upper bound on the run in seconds: a rank still alive then (a hung kernel, a collective whose peer "
+                         "died) prints its Python stacks and exits (0 = off; raise it for very long --steps)")
     ap.add_argument("--i2sb-batch", type=int, default=16,
                     help="config #5 global batch (BASELINE: 128 over 8 GPUs; default 16 = one GPU's share), sharded over the ranks")
     ap.add_argument("--video-eager", action="store_true", help="config #4 with eager launches instead of captured steps")
